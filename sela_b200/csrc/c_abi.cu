@@ -1,0 +1,516 @@
+// c_abi.cu -- the extern "C" boundary declared in include/sela_b200.h.
+//
+// Host-side plumbing only: device selection, a grow-only device workspace, the
+// launches.  No algorithm lives here and there is no CPU fallback: without a
+// CUDA device every compute entry point returns SELAB200_ERR_NO_DEVICE.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kernels.cuh"
+
+using namespace selab200;
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::mutex g_mutex;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(SELAB200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes)
+            return 0;
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        size_t want = need + need / 8 + 4096;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess)
+            return fail(SELAB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        bytes = want;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    DeviceBuffer in, descs, words, work, aux, small;
+    int32_t *h_small = nullptr; // pinned: [0] status, [2..3] words_used
+} g;
+
+const char *status_text(int s)
+{
+    switch (s) {
+    case SELAB200_ERR_CAPACITY: return "output word arena too small";
+    case SELAB200_ERR_RANGE: return "value outside the representable domain (16-bit audio / uint16 word counts)";
+    case SELAB200_ERR_BITSTREAM: return "malformed subframe descriptor or Rice stream";
+    default: return "device reported an error";
+    }
+}
+
+int require_ready()
+{
+    if (!g.ready)
+        return fail(SELAB200_ERR_NOT_INIT, "selab200_init() has not been called (or found no CUDA device)");
+    return 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+template <typename K>
+int set_smem(K kernel, size_t bytes)
+{
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+int launch_check(const char *what)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(SELAB200_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- device-resident cores (no synchronisation) --------------------------
+
+int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *d_descs,
+                  uint32_t *d_words, size_t capacity, uint64_t *d_used, int32_t *d_status, void *d_ws,
+                  size_t ws_bytes, cudaStream_t stream)
+{
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    if (ws_bytes < selab200_encode_workspace_bytes(n_frames, channels))
+        return fail(SELAB200_ERR_ARGUMENT, "encode workspace too small");
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+    CUDA_TRY(cudaMemsetAsync(d_used, 0, sizeof(uint64_t), stream));
+    if (n_frames == 0)
+        return 0;
+    const bool stereo = channels == 2;
+    const size_t n_units = stereo ? n_frames : (size_t)n_frames * channels;
+    CUDA_TRY(cudaMemsetAsync(d_ws, 0, 256 + n_units * 8, stream));
+    EncodeParams p;
+    p.pcm = d_pcm;
+    p.n_frames = n_frames;
+    p.channels = channels;
+    p.descs = d_descs;
+    p.words = d_words;
+    p.capacity = capacity;
+    p.words_used = reinterpret_cast<unsigned long long *>(d_used);
+    p.status = d_status;
+    p.ticket = reinterpret_cast<uint32_t *>(d_ws);
+    p.scan = reinterpret_cast<unsigned long long *>(static_cast<char *>(d_ws) + 256);
+    if (stereo) {
+        constexpr size_t smem = encode_smem_bytes<true>();
+        if (int rc = set_smem(k_encode<true>, smem))
+            return rc;
+        k_encode<true><<<(unsigned)n_units, 96, smem, stream>>>(p);
+    } else {
+        constexpr size_t smem = encode_smem_bytes<false>();
+        if (int rc = set_smem(k_encode<false>, smem))
+            return rc;
+        k_encode<false><<<(unsigned)n_units, 32, smem, stream>>>(p);
+    }
+    return launch_check("k_encode");
+}
+
+int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
+                  const uint32_t *d_words, size_t n_words, int16_t *d_pcm, int32_t *d_status, void *d_ws,
+                  size_t ws_bytes, cudaStream_t stream)
+{
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    if (ws_bytes < selab200_decode_workspace_bytes(n_frames, channels))
+        return fail(SELAB200_ERR_ARGUMENT, "decode workspace too small");
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+    if (n_frames == 0)
+        return 0;
+    const size_t n_sub = (size_t)n_frames * channels;
+    DecodeParams p;
+    p.descs = d_descs;
+    p.n_frames = n_frames;
+    p.channels = channels;
+    p.words = d_words;
+    p.n_words = n_words;
+    p.pcm_out = d_pcm;
+    p.status = d_status;
+    p.ws_q = static_cast<int32_t *>(d_ws);
+    p.ws_res = reinterpret_cast<int32_t *>(static_cast<char *>(d_ws) + align256(n_sub * 128 * 4));
+    const unsigned blocks = (unsigned)((n_sub + 127) / 128);
+    k_rice_decode<<<blocks, 128, 0, stream>>>(p, 0);
+    if (int rc = launch_check("k_rice_decode(refl)"))
+        return rc;
+    k_rice_decode<<<blocks, 128, 0, stream>>>(p, 1);
+    if (int rc = launch_check("k_rice_decode(res)"))
+        return rc;
+    const size_t smem = synthesise_smem_bytes(channels);
+    if (int rc = set_smem(k_synthesise, smem))
+        return rc;
+    k_synthesise<<<n_frames, 32 * channels, smem, stream>>>(p);
+    return launch_check("k_synthesise");
+}
+
+int read_status(cudaStream_t stream, const int32_t *d_status)
+{
+    CUDA_TRY(cudaMemcpyAsync(g.h_small, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (g.h_small[0] != 0)
+        return fail(g.h_small[0], "%s", status_text(g.h_small[0]));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int selab200_abi_version(void) { return SELAB200_ABI_VERSION; }
+const char *selab200_last_error(void) { return g_error; }
+uint64_t selab200_launch_count(void) { return g_launches.load(); }
+
+int selab200_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g.ready && g.device == device)
+        return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SELAB200_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return fail(SELAB200_ERR_ARGUMENT, "device %d out of range (have %d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SELAB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
+                    prop.major, prop.minor);
+    if (!g.stream)
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.h_small)
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_small), 64));
+    if (int rc = g.small.ensure(256))
+        return rc;
+    g.device = device;
+    g.ready = true;
+    return 0;
+}
+
+void selab200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g.ready)
+        return;
+    cudaStreamSynchronize(g.stream);
+    g.in.release();
+    g.descs.release();
+    g.words.release();
+    g.work.release();
+    g.aux.release();
+    g.small.release();
+    if (g.h_small)
+        cudaFreeHost(g.h_small);
+    g.h_small = nullptr;
+    cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.ready = false;
+}
+
+void *selab200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(SELAB200_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void selab200_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+size_t selab200_encode_words_bound(uint32_t n_frames, uint32_t channels)
+{
+    // residues: <= 2048*(1 + 19) + sum(u >> 19) bits with |r| < 2^21 for in-domain audio,
+    // i.e. < 2048*24 bits = 1536 words; reflection coefficients: <= 100*(8+1) bits.
+    return (size_t)n_frames * channels * (1536 + 32) + 64;
+}
+
+size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels)
+{
+    return 256 + (size_t)n_frames * channels * 8 + 256;
+}
+
+size_t selab200_decode_workspace_bytes(uint32_t n_frames, uint32_t channels)
+{
+    const size_t n_sub = (size_t)n_frames * channels;
+    return align256(n_sub * 128 * 4) + align256(n_sub * kFrame * 4) + 256;
+}
+
+int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels,
+                                  selab200_subframe_desc *d_descs, uint32_t *d_words, size_t words_capacity,
+                                  uint64_t *d_words_used, int32_t *d_status, void *d_workspace,
+                                  size_t workspace_bytes, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!d_pcm || !d_descs || !d_words || !d_words_used || !d_status || !d_workspace)
+        return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
+    return encode_device(d_pcm, n_frames, channels, d_descs, d_words, words_capacity, d_words_used, d_status,
+                         d_workspace, workspace_bytes, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
+                                  const uint32_t *d_words, size_t n_words, int16_t *d_pcm_out, int32_t *d_status,
+                                  void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!d_descs || !d_words || !d_pcm_out || !d_status || !d_workspace)
+        return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
+    return decode_device(d_descs, n_frames, channels, d_words, n_words, d_pcm_out, d_status, d_workspace,
+                         workspace_bytes, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
+                           selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
+                           size_t *words_used)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!pcm || !descs || !words || !words_used)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    *words_used = 0;
+    if (n_frames == 0)
+        return 0;
+    const size_t n_sub = (size_t)n_frames * channels;
+    const size_t pcm_bytes = n_sub * kFrame * 2;
+    const size_t ws_bytes = selab200_encode_workspace_bytes(n_frames, channels);
+    if (int rc = g.in.ensure(pcm_bytes)) return rc;
+    if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
+    if (int rc = g.words.ensure(words_capacity * 4 + 16)) return rc;
+    if (int rc = g.work.ensure(ws_bytes)) return rc;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    uint64_t *d_used = reinterpret_cast<uint64_t *>(static_cast<char *>(g.small.ptr) + 8);
+    CUDA_TRY(cudaMemcpyAsync(g.in.ptr, pcm, pcm_bytes, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = encode_device(static_cast<const int16_t *>(g.in.ptr), n_frames, channels,
+                               static_cast<selab200_subframe_desc *>(g.descs.ptr),
+                               static_cast<uint32_t *>(g.words.ptr), words_capacity, d_used, d_status, g.work.ptr,
+                               g.work.bytes, g.stream))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.h_small, g.small.ptr, 16, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(descs, g.descs.ptr, n_sub * sizeof(selab200_subframe_desc), cudaMemcpyDeviceToHost,
+                             g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    uint64_t used;
+    memcpy(&used, g.h_small + 2, 8);
+    if (g.h_small[0] != 0) {
+        *words_used = (size_t)used; // for CAPACITY: the size the caller needs
+        return fail(g.h_small[0], "%s", status_text(g.h_small[0]));
+    }
+    CUDA_TRY(cudaMemcpyAsync(words, g.words.ptr, used * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    *words_used = (size_t)used;
+    return 0;
+}
+
+int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
+                           const uint32_t *words, size_t n_words, int16_t *pcm_out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!descs || !pcm_out || (!words && n_words))
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (n_frames == 0)
+        return 0;
+    const size_t n_sub = (size_t)n_frames * channels;
+    const size_t pcm_bytes = n_sub * kFrame * 2;
+    const size_t ws_bytes = selab200_decode_workspace_bytes(n_frames, channels);
+    if (int rc = g.in.ensure(pcm_bytes)) return rc;
+    if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
+    if (int rc = g.words.ensure(n_words * 4 + 16)) return rc;
+    if (int rc = g.work.ensure(ws_bytes)) return rc;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    CUDA_TRY(cudaMemcpyAsync(g.descs.ptr, descs, n_sub * sizeof(selab200_subframe_desc), cudaMemcpyHostToDevice,
+                             g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.words.ptr, words, n_words * 4, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = decode_device(static_cast<const selab200_subframe_desc *>(g.descs.ptr), n_frames, channels,
+                               static_cast<const uint32_t *>(g.words.ptr), n_words,
+                               static_cast<int16_t *>(g.in.ptr), d_status, g.work.ptr, g.work.bytes, g.stream))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(pcm_out, g.in.ptr, pcm_bytes, cudaMemcpyDeviceToHost, g.stream));
+    return read_status(g.stream, d_status);
+}
+
+// ---------------------------------------------------------------- stages --
+
+int selab200_lpc_residues(const int32_t *samples, uint32_t n_sub, uint8_t *order, int32_t *q, int32_t *residues)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!samples || !order || !q || !residues)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (n_sub == 0)
+        return 0;
+    for (size_t i = 0; i < (size_t)n_sub * kFrame; i++)
+        if (samples[i] > 65535 || samples[i] < -65535)
+            return fail(SELAB200_ERR_RANGE, "sample %zu = %d outside the 17-bit domain of 16-bit audio", i, samples[i]);
+    const size_t sig = (size_t)n_sub * kFrame * 4;
+    if (int rc = g.in.ensure(sig)) return rc;
+    if (int rc = g.work.ensure(sig)) return rc;
+    if (int rc = g.aux.ensure((size_t)n_sub * kMaxOrder * 4 + n_sub + 256)) return rc;
+    int32_t *d_q = static_cast<int32_t *>(g.aux.ptr);
+    uint8_t *d_order = reinterpret_cast<uint8_t *>(d_q + (size_t)n_sub * kMaxOrder);
+    CUDA_TRY(cudaMemcpyAsync(g.in.ptr, samples, sig, cudaMemcpyHostToDevice, g.stream));
+    k_lpc_residues<<<n_sub, 32, 0, g.stream>>>(static_cast<const int32_t *>(g.in.ptr), n_sub, d_order, d_q,
+                                               static_cast<int32_t *>(g.work.ptr));
+    if (int rc = launch_check("k_lpc_residues"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(residues, g.work.ptr, sig, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(q, d_q, (size_t)n_sub * kMaxOrder * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(order, d_order, n_sub, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int selab200_lpc_samples(const int32_t *residues, uint32_t n_sub, const uint8_t *order, const int32_t *q,
+                         int32_t *samples)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!residues || !order || !q || !samples)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (n_sub == 0)
+        return 0;
+    for (uint32_t i = 0; i < n_sub; i++)
+        if (order[i] > kMaxOrder)
+            return fail(SELAB200_ERR_BITSTREAM, "order[%u] = %u exceeds %d", i, order[i], kMaxOrder);
+    const size_t sig = (size_t)n_sub * kFrame * 4;
+    if (int rc = g.in.ensure(sig)) return rc;
+    if (int rc = g.work.ensure(sig)) return rc;
+    if (int rc = g.aux.ensure((size_t)n_sub * kMaxOrder * 4 + n_sub + 256)) return rc;
+    int32_t *d_q = static_cast<int32_t *>(g.aux.ptr);
+    uint8_t *d_order = reinterpret_cast<uint8_t *>(d_q + (size_t)n_sub * kMaxOrder);
+    CUDA_TRY(cudaMemcpyAsync(g.in.ptr, residues, sig, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_q, q, (size_t)n_sub * kMaxOrder * 4, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_order, order, n_sub, cudaMemcpyHostToDevice, g.stream));
+    k_lpc_samples<<<n_sub, 32, 0, g.stream>>>(static_cast<const int32_t *>(g.in.ptr), n_sub, d_order, d_q,
+                                              static_cast<int32_t *>(g.work.ptr));
+    if (int rc = launch_check("k_lpc_samples"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(samples, g.work.ptr, sig, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int selab200_rice_encode(const int32_t *values, const uint32_t *counts, uint32_t n_streams, uint32_t stride,
+                         uint32_t *rice_param, uint32_t *n_words, uint32_t *words, uint32_t words_stride)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!values || !counts || !rice_param || !n_words || !words)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (stride > (uint32_t)kFrame)
+        return fail(SELAB200_ERR_ARGUMENT, "stride %u exceeds %d values per stream", stride, kFrame);
+    for (uint32_t i = 0; i < n_streams; i++)
+        if (counts[i] > stride)
+            return fail(SELAB200_ERR_ARGUMENT, "counts[%u] exceeds stride", i);
+    if (n_streams == 0)
+        return 0;
+    const size_t vbytes = (size_t)n_streams * stride * 4, wbytes = (size_t)n_streams * words_stride * 4;
+    if (int rc = g.in.ensure(vbytes + 16)) return rc;
+    if (int rc = g.words.ensure(wbytes + 16)) return rc;
+    if (int rc = g.aux.ensure((size_t)n_streams * 12 + 256)) return rc;
+    uint32_t *d_counts = static_cast<uint32_t *>(g.aux.ptr);
+    uint32_t *d_k = d_counts + n_streams, *d_nw = d_k + n_streams;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.in.ptr, values, vbytes, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_counts, counts, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
+    k_rice_encode<<<n_streams, 32, 0, g.stream>>>(static_cast<const int32_t *>(g.in.ptr), d_counts, stride, d_k,
+                                                  d_nw, static_cast<uint32_t *>(g.words.ptr), words_stride, d_status);
+    if (int rc = launch_check("k_rice_encode"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(rice_param, d_k, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(n_words, d_nw, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(words, g.words.ptr, wbytes, cudaMemcpyDeviceToHost, g.stream));
+    return read_status(g.stream, d_status);
+}
+
+int selab200_rice_decode(const uint32_t *words, const uint32_t *n_words, uint32_t words_stride,
+                         const uint32_t *rice_param, const uint32_t *counts, uint32_t n_streams, int32_t *out,
+                         uint32_t out_stride)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!words || !n_words || !rice_param || !counts || !out)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (n_streams == 0)
+        return 0;
+    const size_t wbytes = (size_t)n_streams * words_stride * 4, obytes = (size_t)n_streams * out_stride * 4;
+    if (int rc = g.words.ensure(wbytes + 16)) return rc;
+    if (int rc = g.work.ensure(obytes + 16)) return rc;
+    if (int rc = g.aux.ensure((size_t)n_streams * 12 + 256)) return rc;
+    uint32_t *d_nw = static_cast<uint32_t *>(g.aux.ptr);
+    uint32_t *d_k = d_nw + n_streams, *d_counts = d_k + n_streams;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.work.ptr, 0, obytes, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(g.words.ptr, words, wbytes, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_nw, n_words, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_k, rice_param, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_counts, counts, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
+    k_rice_decode_streams<<<(n_streams + 127) / 128, 128, 0, g.stream>>>(
+        static_cast<const uint32_t *>(g.words.ptr), d_nw, words_stride, d_k, d_counts, n_streams,
+        static_cast<int32_t *>(g.work.ptr), out_stride, d_status);
+    if (int rc = launch_check("k_rice_decode_streams"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, g.work.ptr, obytes, cudaMemcpyDeviceToHost, g.stream));
+    return read_status(g.stream, d_status);
+}
+
+} // extern "C"

@@ -1,0 +1,92 @@
+// common.cuh -- shared definitions for the sm_100a kernels of the SELA hot path.
+//
+// One warp owns one subframe (one channel of one 2048-sample frame).  All
+// floating point that feeds the bitstream goes through the *_rn intrinsics below:
+// they are never contracted into FMAs, so every operation rounds exactly once, in
+// the reference's order.  The translation units are also built
+// with -fmad=false as a second line of defence.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/sela_b200.h"
+
+namespace selab200 {
+
+constexpr int kFrame    = SELAB200_FRAME_SAMPLES; // 2048
+constexpr int kMaxOrder = SELAB200_MAX_LPC_ORDER; // 100
+constexpr int kMaxRice  = SELAB200_MAX_RICE_PARAM; // 20 (k searched in [0, 20))
+constexpr int kQ        = 35;                      // CORRECTION_FACTOR, src/include/lpc.hpp:8
+constexpr unsigned kFull = 0xffffffffu;
+
+// Offset that makes every in-domain sample (|s| <= 65535) a non-negative 18-bit
+// number, so int64 x int32 products need one IMAD.WIDE.U32 + one IMAD (see lpc.cuh).
+constexpr int      kSampleBias = 1 << 17;
+constexpr uint32_t kSampleBiasU = 1u << 17;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ double shfl_d(double v, int src)
+{
+    return __shfl_sync(kFull, v, src);
+}
+__device__ __forceinline__ double shfl_down_d(double v, int delta)
+{
+    return __shfl_down_sync(kFull, v, delta);
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src)
+{
+    return __shfl_sync(kFull, v, src);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Inclusive prefix sum over the warp.
+__device__ __forceinline__ uint32_t warp_scan_inclusive_u32(uint32_t v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o)
+            v += t;
+    }
+    return v;
+}
+
+// The signal one warp analyses: a channel of the frame held as int16 in shared
+// memory, or the difference ch0 - ch1 (src/frame/frame_encoder.cpp:20-24).
+struct Signal {
+    const int16_t *a;
+    const int16_t *b; // nullptr unless difference
+    __device__ __forceinline__ int at(int j) const
+    {
+        int v = a[j];
+        if (b)
+            v -= b[j];
+        return v;
+    }
+};
+
+// Device-side status: first error wins (codes are negative, so take the min).
+__device__ __forceinline__ void raise_status(int32_t *status, int code)
+{
+    if (status)
+        atomicMin(status, code);
+}
+
+} // namespace selab200

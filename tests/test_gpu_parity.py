@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import signals
+import sela_b200
+from sela_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FRAME = 2048
+
+
+@pytest.fixture(scope="module")
+def O():
+    return ol.best()
+
+
+def _analyse_all(O, frames):
+    return [O.lpc_analyse(s) for s in frames]
+
+
+def test_lpc_residues_families(O):
+    fam = signals.families()
+    names = sorted(fam)
+    x = np.stack([fam[n] for n in names])
+    order, q, res = sela_b200.lpc_residues(x)
+    for i, n in enumerate(names):
+        a = O.lpc_analyse(x[i])
+        assert order[i] == a["order"], (n, order[i], a["order"])
+        assert np.array_equal(q[i, :a["order"]], a["q"]), n
+        assert not q[i, a["order"]:].any(), n
+        assert np.array_equal(res[i], a["res"]), n
+
+
+def test_lpc_residues_random(O):
+    x = signals.random_frames(192, seed=21)
+    order, q, res = sela_b200.lpc_residues(x)
+    for i in range(x.shape[0]):
+        a = O.lpc_analyse(x[i])
+        assert order[i] == a["order"], i
+        assert np.array_equal(q[i, :a["order"]], a["q"]), i
+        assert np.array_equal(res[i], a["res"]), i
+
+
+def test_lpc_residues_dc_levels(O):
+    """x - mean is rounding noise on constant frames: summation order decides q[0]."""
+    levels = np.array(list(range(-32768, 32768, 131)) + [-1, 1, 32767], np.int32)
+    x = np.repeat(levels[:, None], FRAME, axis=1)
+    order, q, res = sela_b200.lpc_residues(x)
+    for i, lv in enumerate(levels):
+        a = O.lpc_analyse(x[i])
+        assert (order[i], list(q[i, :a["order"]])) == (a["order"], list(a["q"])), lv
+        assert np.array_equal(res[i], a["res"]), lv
+
+
+def test_lpc_difference_domain(O):
+    """17-bit inputs (L-R of two 16-bit channels)."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(-32768, 32768, (16, FRAME))
+    b = rng.integers(-32768, 32768, (16, FRAME))
+    x = (a - b).astype(np.int32)
+    x[0] = 65535
+    x[1] = -65535
+    order, q, res = sela_b200.lpc_residues(x)
+    for i in range(x.shape[0]):
+        r = O.lpc_analyse(x[i])
+        assert order[i] == r["order"] and np.array_equal(q[i, :r["order"]], r["q"])
+        assert np.array_equal(res[i], r["res"])
+
+
+def test_lpc_samples_roundtrip_and_oracle(O):
+    x = np.concatenate([np.stack(list(signals.families().values())), signals.random_frames(64, seed=5)])
+    order, q, res = sela_b200.lpc_residues(x)
+    back = sela_b200.lpc_samples(res, order, q)
+    assert np.array_equal(back, x)
+    # arbitrary (not encoder-produced) residues/coefficients against the oracle's synthesiser
+    rng = np.random.default_rng(9)
+    n = 48
+    res2 = rng.integers(-300, 300, (n, FRAME)).astype(np.int32)
+    order2 = rng.integers(0, 101, n).astype(np.uint8)
+    order2[:4] = [0, 1, 2, 100]
+    q2 = rng.integers(-20, 20, (n, 100)).astype(np.int32)
+    q2[:, 0] = rng.integers(-64, 64, n)
+    q2[:, 1] = rng.integers(-64, 64, n)
+    got = sela_b200.lpc_samples(res2, order2, q2)
+    for i in range(n):
+        want = O.lpc_synthesise(res2[i], int(order2[i]), q2[i, :order2[i]])
+        assert np.array_equal(got[i], want), (i, order2[i])
+
+
+def test_rice_encode_decode(O):
+    rng = np.random.default_rng(13)
+    cases = []
+    for n, scale in [(100, 400), (1, 5), (2048, 3), (2048, 70000), (333, 1 << 20), (17, 0), (2048, 1),
+                     (2047, 900), (31, 100000), (64, 12), (2048, 1 << 17)]:
+        cases.append(rng.integers(-scale, scale + 1, n).astype(np.int32))
+    cases.append((200 + rng.integers(0, 201, 100)).astype(np.int32))      # test/ricetests.cpp:11-13
+    spike = np.zeros(2048, np.int32); spike[5] = 1 << 22; spike[1999] = -(1 << 21)   # long unary runs
+    cases.append(spike)
+    stride = 2048
+    vals = np.zeros((len(cases), stride), np.int32)
+    counts = np.array([c.size for c in cases], np.uint32)
+    for i, c in enumerate(cases):
+        vals[i, :c.size] = c
+    k, nw, words = sela_b200.rice_encode(vals, counts, words_stride=8192)
+    for i, c in enumerate(cases):
+        ko, wo = O.rice_encode(c)
+        assert k[i] == ko, (i, k[i], ko)
+        assert nw[i] == wo.size, (i, nw[i], wo.size)
+        assert np.array_equal(words[i, :nw[i]], wo), i
+    out = sela_b200.rice_decode(words, nw, k, counts, out_stride=stride)
+    for i, c in enumerate(cases):
+        assert np.array_equal(out[i, :c.size], c), i
+
+
+KAT = {
+    "sine_deg": (17, 4, 3, 7, 552, 0xFF6EFF00, 0x00000010, 0x0BC50C3B, 0xFAF0DFE3),
+    "zeros": (1, 0, 1, 0, 64, 0, 0, 0x4B95F515, 0xE6A1D1C5),
+    "dc_1234": (1, 6, 1, 10, 832, 0xCC9664B3, 0x25992CC9, 0x1DAF5698, 0xFF0C5DC5),
+    "cosine_deg": (16, 4, 3, 7, 585, 0xFFFFFFFF, 0x00000019, 0x4F1CBBE0, 0x10A3227D),
+    "impulse0": (1, 5, 1, 4, 448, 0xFFFFFFFF, 0x00000000, 0xBD7CAAD0, 0x266C2942),
+}
+
+
+@pytest.mark.parametrize("name", sorted(KAT))
+def test_kat_mono_frame(name):
+    """SURVEY.md 8(a) known answers, through the batch encoder on a 1-frame mono input (config 1)."""
+    s = signals.families()[name].astype(np.int16)
+    descs, words = sela_b200.encode_frames(s, 1)
+    d = descs[0]
+    wq = words[d["refl_offset"]:d["refl_offset"] + d["refl_words"]]
+    wr = words[d["res_offset"]:d["res_offset"] + d["res_words"]]
+    got = (d["lpc_order"], d["refl_rice_param"], d["refl_words"], d["res_rice_param"], d["res_words"],
+           int(wr[0]), int(wr[-1]), ol.fnv1a32(wq), ol.fnv1a32(wr))
+    assert got == KAT[name]
+    assert np.array_equal(sela_b200.decode_frames(descs, words, 1), s)
+
+
+def _stereo_mix(n_frames, seed):
+    pcm = synth.sine_noise(44100, 2, n_frames=n_frames, seed=seed)
+    f = FRAME
+    if n_frames >= 8:
+        pcm[f * 3:f * 6, 1] = pcm[f * 3:f * 6, 0] - (pcm[f * 3:f * 6, 1] >> 6)  # near-identical -> diff wins
+        pcm[f * 6:f * 7, 1] = pcm[f * 6:f * 7, 0]                                  # identical -> zero diff
+        pcm[f * 7:f * 8, :] = 0                                                     # digital silence
+    return pcm
+
+
+@pytest.mark.parametrize("channels,n_frames", [(1, 9), (2, 24), (3, 5), (8, 4)])
+def test_frames_encode_bit_exact_and_roundtrip(O, channels, n_frames):
+    pcm = _stereo_mix(n_frames, 3) if channels == 2 else synth.sine_noise(48000, channels, n_frames=n_frames, seed=2)
+    d_ref, w_ref = O.encode_frames(pcm, channels)
+    d, w = sela_b200.encode_frames(pcm, channels)
+    assert d.tobytes() == d_ref.tobytes()
+    assert np.array_equal(w, w_ref)
+    if channels == 2:
+        assert set(d["subframe_type"]) == {0, 1}
+    out = sela_b200.decode_frames(d_ref, w_ref, channels)
+    assert np.array_equal(out, pcm.reshape(-1))
+    assert np.array_equal(out, O.decode_frames(d_ref, w_ref, channels))
+
+
+def test_frames_edge_signals_stereo(O):
+    fam = signals.families()
+    names = sorted(fam)
+    rng = np.random.default_rng(1)
+    frames = []
+    for i, n in enumerate(names):
+        other = fam[names[(i * 7 + 3) % len(names)]]
+        frames.append(np.stack([fam[n], other], axis=1))
+    frames.append(np.stack([fam["white_full"], -fam["white_full"] - 1], axis=1))     # inverted channel
+    pcm = np.concatenate(frames).astype(np.int16)
+    d_ref, w_ref = O.encode_frames(pcm, 2)
+    d, w = sela_b200.encode_frames(pcm, 2)
+    assert d.tobytes() == d_ref.tobytes()
+    assert np.array_equal(w, w_ref)
+    assert np.array_equal(sela_b200.decode_frames(d, w, 2), pcm.reshape(-1))
+
+
+def test_decode_rejects_malformed(O):
+    pcm = synth.sine_noise(44100, 2, n_frames=2, seed=4)
+    d, w = sela_b200.encode_frames(pcm, 2)
+    for field, value in [("lpc_order", 101), ("res_rice_param", 40), ("channel", 7), ("samples", 100),
+                         ("res_offset", 1 << 40)]:
+        bad = d.copy()
+        bad[field][1] = value
+        with pytest.raises(sela_b200.SelaB200Error) as e:
+            sela_b200.decode_frames(bad, w, 2)
+        assert e.value.status == -6
+    dup = d.copy()
+    dup["channel"][1] = dup["channel"][0]
+    with pytest.raises(sela_b200.SelaB200Error):
+        sela_b200.decode_frames(dup, w, 2)
+    # truncated arena: must not fault, must report
+    with pytest.raises(sela_b200.SelaB200Error):
+        sela_b200.decode_frames(d, w[: w.size // 2], 2)
+
+
+def test_encode_capacity_error():
+    pcm = synth.sine_noise(44100, 2, n_frames=4, seed=4)
+    with pytest.raises(sela_b200.SelaB200Error) as e:
+        sela_b200.encode_frames(pcm, 2, words_capacity=100)
+    assert e.value.status == -4
+    d, w = sela_b200.encode_frames(pcm, 2)       # and the library still works afterwards
+    assert np.array_equal(sela_b200.decode_frames(d, w, 2), pcm.reshape(-1))
+
+
+def test_empty_batch():
+    d, w = sela_b200.encode_frames(np.zeros(0, np.int16), 2)
+    assert d.size == 0 and w.size == 0
+    assert sela_b200.decode_frames(d, w, 2).size == 0
+
+
+def test_large_batch_properties(O):
+    """BASELINE config-2/3 shape at reduced length (60 s): oracle equality on a sampled subset of
+    frames, plus the size-independent properties on everything: exact round trip and
+    offsets forming a gap-free prefix sum."""
+    pcm = synth.sine_noise(44100, 2, seconds=60, seed=1)
+    n_frames = pcm.shape[0] // FRAME
+    d, w = sela_b200.encode_frames(pcm, 2)
+    sizes = d["refl_words"].astype(np.int64) + d["res_words"]
+    assert np.array_equal(d["refl_offset"], np.concatenate([[0], np.cumsum(sizes)[:-1]]))
+    assert np.array_equal(d["res_offset"], d["refl_offset"] + d["refl_words"])
+    assert w.size == sizes.sum()
+    assert np.array_equal(sela_b200.decode_frames(d, w, 2), pcm.reshape(-1))
+    pick = np.linspace(0, n_frames - 1, 40).astype(int)
+    for f in pick:
+        dr, wr = O.encode_frames(pcm[f * FRAME:(f + 1) * FRAME], 2, threads=1)
+        for c in range(2):
+            a, b = d[2 * f + c], dr[c]
+            for name in ("channel", "subframe_type", "parent_channel", "refl_rice_param", "refl_words",
+                         "lpc_order", "res_rice_param", "res_words", "samples"):
+                assert a[name] == b[name], (f, c, name)
+            assert np.array_equal(w[a["refl_offset"]:a["refl_offset"] + sizes[2 * f + c]],
+                                  wr[b["refl_offset"]:b["refl_offset"] + sizes[2 * f + c]]), (f, c)

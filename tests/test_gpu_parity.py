@@ -76,7 +76,14 @@ def test_lpc_samples_roundtrip_and_oracle(O):
     x = np.concatenate([np.stack(list(signals.families().values())), signals.random_frames(64, seed=5)])
     order, q, res = sela_b200.lpc_residues(x)
     back = sela_b200.lpc_samples(res, order, q)
-    assert np.array_equal(back, x)
+    lossless = 0
+    for i in range(x.shape[0]):
+        # the reference decoder is the contract: encoder rounds (c+P)>>35, decoder -((c-P)>>35),
+        # which differ when P mod 2^35 == 2^34 -- e.g. the sparse-spike frame here
+        want = O.lpc_synthesise(res[i], int(order[i]), q[i, :order[i]])
+        assert np.array_equal(back[i], want), i
+        lossless += bool(np.array_equal(want, x[i]))
+    assert lossless >= x.shape[0] - 2
     # arbitrary (not encoder-produced) residues/coefficients against the oracle's synthesiser
     rng = np.random.default_rng(9)
     n = 48
@@ -235,5 +242,6 @@ def test_large_batch_properties(O):
             for name in ("channel", "subframe_type", "parent_channel", "refl_rice_param", "refl_words",
                          "lpc_order", "res_rice_param", "res_words", "samples"):
                 assert a[name] == b[name], (f, c, name)
-            assert np.array_equal(w[a["refl_offset"]:a["refl_offset"] + sizes[2 * f + c]],
-                                  wr[b["refl_offset"]:b["refl_offset"] + sizes[2 * f + c]]), (f, c)
+            n = int(sizes[2 * f + c])
+            o1, o2 = int(a["refl_offset"]), int(b["refl_offset"])
+            assert np.array_equal(w[o1:o1 + n], wr[o2:o2 + n]), (f, c)

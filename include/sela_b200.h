@@ -79,6 +79,10 @@ int  selab200_abi_version(void);
 /* Number of kernel launches issued by this process so far (bench bookkeeping). */
 uint64_t selab200_launch_count(void);
 
+/* Device self-test: counts inputs s in [-65535, 65535] for which the kernels'
+ * division-free s/32767 differs from IEEE division (must be 0). */
+int selab200_selftest(uint32_t *mismatches);
+
 /* Pinned host memory for the host-buffer calls (pageable memory also works, slower). */
 void *selab200_host_alloc(size_t bytes);
 void  selab200_host_free(void *p);
@@ -113,7 +117,7 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
                            int16_t *pcm_out);
 
 /* Device-resident forms: every pointer is a device pointer, work is enqueued on
- * `stream` (a cudaStream_t, may be NULL for the library stream) and the call
+ * `stream` (a cudaStream_t; NULL is the legacy default stream, as everywhere in CUDA) and the call
  * returns without synchronising.  d_status (int32, device) receives 0 or a
  * selab200_status once the stream has drained; d_words_used is a device uint64.
  * workspace: selab200_*_workspace_bytes() bytes of device memory, 256-aligned. */

@@ -294,7 +294,7 @@ int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint3
     if (!d_pcm || !d_descs || !d_words || !d_words_used || !d_status || !d_workspace)
         return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
     return encode_device(d_pcm, n_frames, channels, d_descs, d_words, words_capacity, d_words_used, d_status,
-                         d_workspace, workspace_bytes, stream ? (cudaStream_t)stream : g.stream);
+                         d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
@@ -307,7 +307,7 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
     if (!d_descs || !d_words || !d_pcm_out || !d_status || !d_workspace)
         return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
     return decode_device(d_descs, n_frames, channels, d_words, n_words, d_pcm_out, d_status, d_workspace,
-                         workspace_bytes, stream ? (cudaStream_t)stream : g.stream);
+                         workspace_bytes, (cudaStream_t)stream);
 }
 
 int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
@@ -380,6 +380,24 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
         return rc;
     CUDA_TRY(cudaMemcpyAsync(pcm_out, g.in.ptr, pcm_bytes, cudaMemcpyDeviceToHost, g.stream));
     return read_status(g.stream, d_status);
+}
+
+int selab200_selftest(uint32_t *mismatches)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!mismatches)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    uint32_t *d = reinterpret_cast<uint32_t *>(static_cast<char *>(g.small.ptr) + 32);
+    CUDA_TRY(cudaMemsetAsync(d, 0, 4, g.stream));
+    k_selftest_scaling<<<(131071 + 255) / 256, 256, 0, g.stream>>>(d);
+    if (int rc = launch_check("k_selftest_scaling"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(g.h_small + 8, d, 4, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    *mismatches = (uint32_t)g.h_small[8];
+    return 0;
 }
 
 // ---------------------------------------------------------------- stages --

@@ -68,8 +68,21 @@ __device__ __forceinline__ uint32_t warp_scan_inclusive_u32(uint32_t v)
     return v;
 }
 
+// Every signal buffer in shared memory is preceded by kHistoryPad zero samples: the
+// history "before the frame" that the filters read as s = 0.
+constexpr int kHistoryPad = 128;
+
+__device__ __forceinline__ void unpack8(const uint4 v, int (&s)[8])
+{
+    s[0] = (int)(v.x << 16) >> 16; s[1] = (int)v.x >> 16;
+    s[2] = (int)(v.y << 16) >> 16; s[3] = (int)v.y >> 16;
+    s[4] = (int)(v.z << 16) >> 16; s[5] = (int)v.z >> 16;
+    s[6] = (int)(v.w << 16) >> 16; s[7] = (int)v.w >> 16;
+}
+
 // The signal one warp analyses: a channel of the frame held as int16 in shared
 // memory, or the difference ch0 - ch1 (src/frame/frame_encoder.cpp:20-24).
+// a/b point at sample 0 (16-byte aligned, kHistoryPad zeros in front).
 struct Signal {
     const int16_t *a;
     const int16_t *b; // nullptr unless difference
@@ -79,6 +92,37 @@ struct Signal {
         if (b)
             v -= b[j];
         return v;
+    }
+    // samples [8g, 8g+8) biased by 2^17 (g >= -kHistoryPad/8)
+    __device__ __forceinline__ void load8(int g, uint32_t (&w)[8]) const
+    {
+        int s[8];
+        unpack8(*reinterpret_cast<const uint4 *>(a + 8 * g), s);
+        if (b) {
+            int t[8];
+            unpack8(*reinterpret_cast<const uint4 *>(b + 8 * g), t);
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                s[r] -= t[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            w[r] = (uint32_t)(s[r] + kSampleBias);
+    }
+};
+
+// int32 signal in shared memory (stage-level entry points), same conventions.
+struct PlainSignal {
+    const int32_t *s;
+    __device__ __forceinline__ int at(int j) const { return s[j]; }
+    __device__ __forceinline__ void load8(int g, uint32_t (&w)[8]) const
+    {
+        const int4 v0 = *reinterpret_cast<const int4 *>(s + 8 * g);
+        const int4 v1 = *reinterpret_cast<const int4 *>(s + 8 * g + 4);
+        w[0] = (uint32_t)(v0.x + kSampleBias); w[1] = (uint32_t)(v0.y + kSampleBias);
+        w[2] = (uint32_t)(v0.z + kSampleBias); w[3] = (uint32_t)(v0.w + kSampleBias);
+        w[4] = (uint32_t)(v1.x + kSampleBias); w[5] = (uint32_t)(v1.y + kSampleBias);
+        w[6] = (uint32_t)(v1.z + kSampleBias); w[7] = (uint32_t)(v1.w + kSampleBias);
     }
 };
 

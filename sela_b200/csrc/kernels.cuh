@@ -93,11 +93,12 @@ __global__ void __launch_bounds__(STEREO ? 96 : 32) k_encode(EncodeParams p)
 {
     constexpr int kWarps = STEREO ? 3 : 1;
     constexpr int kChan = STEREO ? 2 : 1; // channels held in shared memory per CTA
+    constexpr int kRow = kHistoryPad + kFrame;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                       // [kChan][2048]
-    LpcSmem *lpc_all = reinterpret_cast<LpcSmem *>(smem_raw + kChan * kFrame * 2);
-    int32_t *res_all = reinterpret_cast<int32_t *>(lpc_all + kWarps);           // [kWarps][2048]
-    SubframeResult *results = reinterpret_cast<SubframeResult *>(res_all + kWarps * kFrame);
+    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                        // [kChan][pad + 2048]
+    WarpScratch *scratch_all = reinterpret_cast<WarpScratch *>(smem_raw + kChan * kRow * 2);
+    CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(scratch_all + kWarps);
+    SubframeResult *results = reinterpret_cast<SubframeResult *>(coef_all + kWarps);
     unsigned long long *base_slot = reinterpret_cast<unsigned long long *>(results + 4);
     uint32_t *unit_slot = reinterpret_cast<uint32_t *>(base_slot + 1);
 
@@ -112,39 +113,48 @@ __global__ void __launch_bounds__(STEREO ? 96 : 32) k_encode(EncodeParams p)
     const uint32_t frame = STEREO ? unit : unit / p.channels;
     const uint32_t chan0 = STEREO ? 0 : unit % p.channels;
 
-    // ---- stage the PCM of this unit (de-interleave to planar int16) ----
+    // ---- stage the PCM of this unit (de-interleave to planar int16, zero history in front) ----
     const int16_t *src = p.pcm + (size_t)frame * kFrame * p.channels;
+    for (int j = threadIdx.x; j < kChan * kHistoryPad / 2; j += blockDim.x) {
+        const int c = j / (kHistoryPad / 2), o = j % (kHistoryPad / 2);
+        reinterpret_cast<uint32_t *>(s16 + c * kRow)[o] = 0;
+    }
+    int16_t *ch0 = s16 + kHistoryPad;
     if (STEREO) {
-        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
-        for (int j = threadIdx.x; j < kFrame; j += blockDim.x) {
-            uint32_t v = src32[j];
-            s16[j] = (int16_t)(v & 0xffff);
-            s16[kFrame + j] = (int16_t)(v >> 16);
+        int16_t *ch1 = ch0 + kRow;
+        const uint4 *src128 = reinterpret_cast<const uint4 *>(src); // 4 stereo sample pairs per load
+        for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) {
+            const uint4 v = src128[j];
+            const uint32_t l0 = __byte_perm(v.x, v.y, 0x5410), r0 = __byte_perm(v.x, v.y, 0x7632);
+            const uint32_t l1 = __byte_perm(v.z, v.w, 0x5410), r1 = __byte_perm(v.z, v.w, 0x7632);
+            reinterpret_cast<uint2 *>(ch0)[j] = make_uint2(l0, l1);
+            reinterpret_cast<uint2 *>(ch1)[j] = make_uint2(r0, r1);
         }
     } else {
         for (int j = threadIdx.x; j < kFrame; j += blockDim.x)
-            s16[j] = src[(size_t)j * p.channels + chan0];
+            ch0[j] = src[(size_t)j * p.channels + chan0];
     }
     __syncthreads();
 
     // ---- per-warp analysis ----
     Signal sig;
     if (STEREO) {
-        sig.a = (warp == 1) ? s16 + kFrame : s16;
-        sig.b = (warp == 2) ? s16 + kFrame : nullptr;
+        sig.a = (warp == 1) ? ch0 + kRow : ch0;
+        sig.b = (warp == 2) ? ch0 + kRow : nullptr;
     } else {
-        sig.a = s16;
+        sig.a = ch0;
         sig.b = nullptr;
     }
-    LpcSmem &sm = lpc_all[warp];
-    int32_t *res = res_all + warp * kFrame;
-    warp_autocorrelation(sig, sm);
-    warp_schur(sm);
-    const int order = warp_order_and_quantise(sm);
-    warp_coefficients(sm.cf, order);
-    warp_fir_residual(sig, sm.cf, order, res);
+    WarpScratch &scratch = scratch_all[warp];
+    CoefSmem &cf = coef_all[warp];
+    int32_t *res = scratch.res;
+    warp_autocorrelation(sig, scratch.a);
+    warp_schur(scratch.a);
+    const int order = warp_order_and_quantise(scratch.a, cf);
+    warp_coefficients(cf, scratch.a.t, order);
+    warp_fir_residual(sig, cf, order, res);
 
-    const int32_t *qv = sm.cf.q;
+    const int32_t *qv = cf.q;
     auto q_at = [qv](int i) { return qv[i]; };
     auto r_at = [res](int i) { return res[i]; };
     SubframeResult mine;
@@ -209,7 +219,7 @@ constexpr size_t encode_smem_bytes()
 {
     constexpr int kWarps = STEREO ? 3 : 1;
     constexpr int kChan = STEREO ? 2 : 1;
-    return (size_t)kChan * kFrame * 2 + kWarps * (sizeof(LpcSmem) + kFrame * 4) +
+    return (size_t)kChan * (kHistoryPad + kFrame) * 2 + kWarps * (sizeof(WarpScratch) + sizeof(CoefSmem)) +
            4 * sizeof(SubframeResult) + 16;
 }
 
@@ -266,7 +276,8 @@ __global__ void k_synthesise(DecodeParams p)
     const uint32_t ch = p.channels;
     int32_t *planes = reinterpret_cast<int32_t *>(smem_raw);                  // [ch][2048], by channel
     CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(planes + (size_t)ch * kFrame);
-    int *meta = reinterpret_cast<int *>(coef_all + ch); // [ch] type, [ch] parent, [1] valid
+    double *t_all = reinterpret_cast<double *>(coef_all + ch);                // [ch][104]
+    int *meta = reinterpret_cast<int *>(t_all + (size_t)ch * 104); // [ch] type, [ch] parent, [1] valid
 
     const uint32_t frame = blockIdx.x;
     const int warp = warp_id(), lane = lane_id();
@@ -314,7 +325,7 @@ __global__ void k_synthesise(DecodeParams p)
             buf[i] = r[i];
         __syncwarp();
         // order 0 behaves like order 1 with a zero predictor (linear_predictor.cpp:19-22)
-        warp_coefficients(cf, order);
+        warp_coefficients(cf, t_all + warp * 104, order);
         warp_iir_synthesis(cf, order, buf, kFrame);
     }
     __syncthreads();
@@ -331,38 +342,36 @@ __global__ void k_synthesise(DecodeParams p)
 
 inline size_t synthesise_smem_bytes(uint32_t ch)
 {
-    return (size_t)ch * kFrame * 4 + ch * sizeof(CoefSmem) + (2 * ch + 1) * sizeof(int);
+    return (size_t)ch * kFrame * 4 + ch * (sizeof(CoefSmem) + 104 * sizeof(double)) + (2 * ch + 1) * sizeof(int);
 }
 
 // ------------------------------------------------------------ stage level --
-
-struct PlainSignal {
-    const int32_t *s;
-    __device__ __forceinline__ int at(int j) const { return s[j]; }
-};
 
 // lpc::ResidueGenerator::process for one signal per (1-warp) CTA.
 __global__ void __launch_bounds__(32) k_lpc_residues(const int32_t *samples, uint32_t n_sub, uint8_t *order_out,
                                                      int32_t *q_out, int32_t *residues)
 {
-    __shared__ LpcSmem sm;
-    __shared__ int32_t s[kFrame];
-    __shared__ int32_t res[kFrame];
+    __shared__ __align__(16) WarpScratch scratch;
+    __shared__ __align__(16) CoefSmem cf;
+    __shared__ __align__(16) int32_t s_pad[kHistoryPad + kFrame];
     const uint32_t sub = blockIdx.x;
     const int lane = lane_id();
+    int32_t *s = s_pad + kHistoryPad;
+    for (int i = lane; i < kHistoryPad; i += 32)
+        s_pad[i] = 0;
     for (int i = lane; i < kFrame; i += 32)
         s[i] = samples[(size_t)sub * kFrame + i];
     __syncwarp();
     PlainSignal sig{s};
-    warp_autocorrelation(sig, sm);
-    warp_schur(sm);
-    const int order = warp_order_and_quantise(sm);
-    warp_coefficients(sm.cf, order);
-    warp_fir_residual(sig, sm.cf, order, res);
+    warp_autocorrelation(sig, scratch.a);
+    warp_schur(scratch.a);
+    const int order = warp_order_and_quantise(scratch.a, cf);
+    warp_coefficients(cf, scratch.a.t, order);
+    warp_fir_residual(sig, cf, order, scratch.res);
     for (int i = lane; i < kFrame; i += 32)
-        residues[(size_t)sub * kFrame + i] = res[i];
+        residues[(size_t)sub * kFrame + i] = scratch.res[i];
     for (int i = lane; i < kMaxOrder; i += 32)
-        q_out[(size_t)sub * kMaxOrder + i] = i < order ? sm.cf.q[i] : 0;
+        q_out[(size_t)sub * kMaxOrder + i] = i < order ? cf.q[i] : 0;
     if (lane == 0)
         order_out[sub] = (uint8_t)order;
 }
@@ -371,8 +380,9 @@ __global__ void __launch_bounds__(32) k_lpc_residues(const int32_t *samples, uin
 __global__ void __launch_bounds__(32) k_lpc_samples(const int32_t *residues, uint32_t n_sub, const uint8_t *order_in,
                                                     const int32_t *q_in, int32_t *samples)
 {
-    __shared__ CoefSmem cf;
-    __shared__ int32_t buf[kFrame];
+    __shared__ __align__(16) CoefSmem cf;
+    __shared__ double t[104];
+    __shared__ __align__(16) int32_t buf[kFrame];
     const uint32_t sub = blockIdx.x;
     const int lane = lane_id();
     int order = order_in[sub];
@@ -383,10 +393,20 @@ __global__ void __launch_bounds__(32) k_lpc_samples(const int32_t *residues, uin
     for (int i = lane; i < kFrame; i += 32)
         buf[i] = residues[(size_t)sub * kFrame + i];
     __syncwarp();
-    warp_coefficients(cf, order);
+    warp_coefficients(cf, t, order);
     warp_iir_synthesis(cf, order, buf, kFrame);
     for (int i = lane; i < kFrame; i += 32)
         samples[(size_t)sub * kFrame + i] = buf[i];
+}
+
+// Exhaustive device check of sample_to_x against IEEE division over |s| <= 65535.
+__global__ void k_selftest_scaling(uint32_t *mismatches)
+{
+    const int s = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 65535;
+    if (s > 65535)
+        return;
+    if (__double_as_longlong(sample_to_x(s)) != __double_as_longlong(sample_to_x_div(s)))
+        atomicAdd(mismatches, 1u);
 }
 
 // rice::RiceEncoder::process, one stream per (1-warp) CTA.

@@ -11,19 +11,28 @@
 
 namespace selab200 {
 
-// Per-warp shared-memory workspace: predictor (shared by encoder and decoder) ...
+// Per-warp shared memory.  The predictor (shared by encoder and decoder):
 struct CoefSmem {
-    double  t[104];      // step-up scratch
-    long long c[104];    // Q35 coefficients c[0..order]
-    int32_t q[104];      // quantised reflection coefficients
+    long long c[104];            // Q35 coefficients c[0..order], zero above
+    uint32_t clo[112];           // low / high words of c[1..], tap j at index j-1, zero padded:
+    int32_t  chi[112];           //   the FIR / IIR read them in blocks of 8
+    unsigned long long pre[104]; // IIR warm-up: 2^34 + BIAS * sum_{j<=t} c[j]   (t = 0..order)
+    int32_t q[104];              // quantised reflection coefficients
 };
-// ... and the analysis path on top of it.
-struct LpcSmem {
-    double  ring[512];   // x tile for the mean pass, then the d = x - mean ring (swizzled)
-    double  ac[128];     // autocorrelation (raw, then normalised)
-    double  kk[104];     // reflection coefficients k[0..99]
-    CoefSmem cf;
+// Analysis scratch; dead once the predictor exists, so it shares its bytes with the
+// residual buffer the FIR fills afterwards.
+struct AnalysisScratch {
+    double ring[512]; // x tile for the mean pass, then the d = x - mean ring (swizzled)
+    double ac[128];   // autocorrelation (raw, then normalised)
+    double kk[104];   // reflection coefficients k[0..99]
+    double t[104];    // step-up scratch
 };
+union WarpScratch {
+    AnalysisScratch a;
+    int32_t res[kFrame];
+};
+static_assert(sizeof(AnalysisScratch) <= sizeof(int32_t) * kFrame, "analysis scratch must fit under the residuals");
+using LpcSmem = AnalysisScratch;
 
 // ---------------------------------------------------------------------------
 // ring addressing: 512 doubles = 256 chunks of 16 B.  Odd 128-byte rows have
@@ -39,8 +48,20 @@ __device__ __forceinline__ int ring_index(int p) // logical sample index (may be
     return (ring_chunk(p >> 1) << 1) | (p & 1);
 }
 
-// x[j] = (double)s[j] / 32767  (quantizeSamples, residue_generator.cpp:12-18)
-__device__ __forceinline__ double sample_to_x(int s) { return ddiv((double)s, 32767.0); }
+// x[j] = (double)s[j] / 32767  (quantizeSamples, residue_generator.cpp:12-18).
+// Correctly rounded quotient without the division subroutine: q0 = s*rcp, one exact
+// FMA residual, one FMA correction (Markstein).  Equality with IEEE division is
+// verified EXHAUSTIVELY over the whole input domain |s| <= 65535 -- on the CPU in
+// tests/test_host_logic.py and on the device by selab200_selftest().
+__device__ __forceinline__ double sample_to_x(int s)
+{
+    const double rcp = 1.0 / 32767.0;
+    const double a = (double)s;
+    const double q0 = __dmul_rn(a, rcp);
+    const double r = __fma_rn(-q0, 32767.0, a);
+    return __fma_rn(r, rcp, q0);
+}
+__device__ __forceinline__ double sample_to_x_div(int s) { return ddiv((double)s, 32767.0); }
 
 // ---------------------------------------------------------------------------
 // K1: mean-removed autocorrelation, lags 0..100, + normalisation.
@@ -77,7 +98,7 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
         }
         __syncwarp();
     }
-    const double mean = ddiv(sum, (double)kFrame);
+    const double mean = ddiv(sum, (double)kFrame); // exact: power of two
 
     // ---- autocorrelation ----
     // logical d[-128..-1] = 0  -> chunks 192..255
@@ -196,7 +217,7 @@ __device__ void warp_schur(LpcSmem &sm)
 // ---------------------------------------------------------------------------
 // K2b: order selection + 7-bit quantisation
 // generateoptimalLpcOrder / quantizeReflectionCoefficients (residue_generator.cpp:70-96).
-__device__ int warp_order_and_quantise(LpcSmem &sm)
+__device__ int warp_order_and_quantise(const LpcSmem &sm, CoefSmem &cf)
 {
     const int lane = lane_id();
     int best = -1;
@@ -222,9 +243,9 @@ __device__ int warp_order_and_quantise(LpcSmem &sm)
                 v = floor(dmul(64.0, dadd(-1.0, dmul(sqrt2, dsqrt(dadd(-kv, 1.0))))));
             else
                 v = floor(dmul(64.0, kv));
-            sm.cf.q[i] = isnan(v) ? 0 : __double2int_rz(v);
+            cf.q[i] = isnan(v) ? 0 : __double2int_rz(v);
         } else if (i < 104) {
-            sm.cf.q[i] = 0;
+            cf.q[i] = 0;
         }
     }
     __syncwarp();
@@ -248,62 +269,117 @@ __device__ __forceinline__ double dequantise(int i, int q)
     return (double)(idx - 64) / 64.0; // exact
 }
 
-__device__ void warp_coefficients(CoefSmem &sm, int order)
+__device__ void warp_coefficients(CoefSmem &cf, double *t, int order)
 {
     const int lane = lane_id();
-    if (order <= 1) {
-        // a single zero reflection coefficient (linear_predictor.cpp:19-22)
-        if (lane == 0) {
-            sm.c[0] = 0;
-            sm.c[1] = 0;
-        }
-        __syncwarp();
-        return;
+    for (int i = lane; i < 112; i += 32) {
+        cf.clo[i] = 0;
+        cf.chi[i] = 0;
+        if (i < 104)
+            cf.c[i] = 0;
     }
+    __syncwarp();
+    if (order <= 1)
+        return; // a single zero reflection coefficient -> c[1] = 0 (linear_predictor.cpp:19-22)
     for (int i = 0; i < order; i++) {
-        const double ki = dequantise(i, sm.q[i]);
+        const double ki = dequantise(i, cf.q[i]);
         const int half = i >> 1;
         for (int j = lane; j < half; j += 32) {
-            double a = sm.t[j];
-            double b = sm.t[i - 1 - j];
-            sm.t[j] = dadd(a, dmul(ki, b));
-            sm.t[i - 1 - j] = dadd(b, dmul(ki, a));
+            double a = t[j];
+            double b = t[i - 1 - j];
+            t[j] = dadd(a, dmul(ki, b));
+            t[i - 1 - j] = dadd(b, dmul(ki, a));
         }
         if (lane == 0) {
             if (i & 1) {
-                double mid = sm.t[half];
-                sm.t[half] = dadd(mid, dmul(mid, ki));
+                double mid = t[half];
+                t[half] = dadd(mid, dmul(mid, ki));
             }
-            sm.t[i] = ki;
+            t[i] = ki;
         }
         __syncwarp();
     }
     const double scale = 34359738368.0; // 2^35
-    for (int m = lane; m < order; m += 32)
-        sm.c[1 + m] = __double2ll_rz(dmul(scale, -sm.t[m]));
-    if (lane == 0)
-        sm.c[0] = 0;
+    for (int m = lane; m < order; m += 32) {
+        const long long v = __double2ll_rz(dmul(scale, -t[m]));
+        cf.c[1 + m] = v;
+        cf.clo[m] = (uint32_t)v;
+        cf.chi[m] = (int32_t)(v >> 32);
+    }
     __syncwarp();
 }
 
+// Signals hand the filters 8 consecutive samples at a time, biased by 2^17 so that
+// they are non-negative 18-bit numbers: c*s' then needs one IMAD.WIDE.U32 (low word)
+// and one IMAD (high word), and the bias is taken out once per output:
+//   sum_j c[j]*s[i-j] = sum_j c[j]*s'[i-j] - 2^17 * sum_j c[j].
+// Group g covers samples [8g, 8g+8); negative groups (history before the frame) read
+// the zero padding in front of every channel, i.e. s = 0, as the reference's warm-up
+// loop implies.
 // ---------------------------------------------------------------------------
 // K3: integer FIR residual.  generateResidues (residue_generator.cpp:98-119):
 //   r[i] = s[i] - (int32)((2^34 + sum_{j=1..order} c[j]*s[i-j]) >> 35),  s[<0] = 0
-// (the warm-up loop of the reference is the same sum with the missing history
-// read as zero).  Integer adds wrap identically in any order, so the taps are
-// free to be evaluated in any arrangement.
+// Integer adds wrap identically in any order.  Lane l computes 8 consecutive outputs
+// per pass with a 16-sample register window that slides 8 taps per iteration: per 64
+// multiply-accumulates the lane issues 128 IMADs, one 16-byte sample load and four
+// broadcast coefficient loads.
 template <typename Sig>
-__device__ void warp_fir_residual(const Sig &sig, const CoefSmem &sm, int order, int32_t *res)
+__device__ void warp_fir_residual(const Sig &sig, const CoefSmem &cf, int order, int32_t *res)
 {
     const int lane = lane_id();
-    const long long half = 1ll << (kQ - 1);
-    for (int base = 0; base < kFrame; base += 32) {
-        const int i = base + lane;
-        long long acc = half;
-        const int taps = order < i ? order : i;
-        for (int j = 1; j <= taps; j++)
-            acc += sm.c[j] * (long long)sig.at(i - j);
-        res[i] = sig.at(i) - (int32_t)(acc >> kQ);
+    const int nblk = (order + 7) >> 3;
+    long long csum = 0;
+    for (int j = lane + 1; j <= order; j += 32)
+        csum += cf.c[j];
+    csum = (long long)warp_sum_u64((unsigned long long)csum);
+    const unsigned long long corr = (1ull << (kQ - 1)) - ((unsigned long long)csum << 17);
+    const uint4 *clo4 = reinterpret_cast<const uint4 *>(cf.clo);
+    const int4 *chi4 = reinterpret_cast<const int4 *>(cf.chi);
+
+    for (int pass = 0; pass < kFrame / 256; pass++) {
+        const int g0 = pass * 32 + lane;
+        uint32_t hi[8], own[8];
+        sig.load8(g0, hi);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            own[r] = hi[r];
+        unsigned long long alo[8];
+        uint32_t ahi[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            alo[r] = 0;
+            ahi[r] = 0;
+        }
+        for (int t = 0; t < nblk; t++) {
+            uint32_t lo[8];
+            sig.load8(g0 - t - 1, lo);
+            const uint4 l0 = clo4[2 * t], l1 = clo4[2 * t + 1];
+            const int4 h0 = chi4[2 * t], h1 = chi4[2 * t + 1];
+            const uint32_t cl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const int32_t ch[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int tau = 0; tau < 8; tau++) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int idx = 7 + r - tau; // window position of s[i0 + r - (8t + 1 + tau)]
+                    const uint32_t w = idx < 8 ? lo[idx] : hi[idx - 8];
+                    alo[r] += (unsigned long long)cl[tau] * w;
+                    ahi[r] += (uint32_t)ch[tau] * w;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                hi[r] = lo[r];
+        }
+        int32_t out[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const unsigned long long p = alo[r] + ((unsigned long long)ahi[r] << 32) + corr;
+            out[r] = ((int)own[r] - kSampleBias) - (int32_t)((long long)p >> kQ);
+        }
+        int4 *dst = reinterpret_cast<int4 *>(res + 8 * g0);
+        dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_int4(out[4], out[5], out[6], out[7]);
     }
     __syncwarp();
 }
@@ -312,34 +388,132 @@ __device__ void warp_fir_residual(const Sig &sig, const CoefSmem &sm, int order,
 // K6: integer IIR synthesis.  SampleGenerator::generateSamples
 // (src/lpc/sample_generator.cpp:11-30):
 //   s[i] = r[i] - (int)((2^34 - sum_{j=1..order} c[j]*s[i-j]) >> 35),  s[<0] = 0
-// A true recurrence: the warp splits the TAPS (lane l owns taps l+1, l+33, ...),
-// reduces the 64-bit partial sums with shuffles, and lane 0 finishes the sample.
-// `buf` holds r on entry and s on exit (in place).
-__device__ void warp_iir_synthesis(const CoefSmem &sm, int order, int32_t *buf, int n)
+// A true recurrence, evaluated in TRANSPOSED form: lane l owns taps TPL*l+1..TPL*l+TPL
+// and the partial sums of the outputs those taps will feed next.  When s[i] becomes
+// known every lane adds c[j]*s'[i] to the accumulator of output i+j; the accumulator
+// of output i+1 (tap 1, lane 0) is then complete, lane 0 finishes the sample and
+// broadcasts it, and every accumulator moves one tap down (one 64-bit shuffle per
+// lane, register renaming inside a lane).  Critical path per sample: one IMAD, a
+// 64-bit subtract, a shift and ONE shuffle -- instead of a five-level reduction.
+__device__ void warp_iir_prepare(CoefSmem &cf, int order)
+{
+    // pre[t] = 2^34 + 2^17 * sum_{j=1..t} c[j]: removes the sample bias for output t
+    // (during warm-up only taps j <= t have seen a real sample)
+    const int lane = lane_id();
+    long long v[4], run = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int j = 4 * lane + m + 1;
+        run += (j <= order) ? cf.c[j] : 0;
+        v[m] = run;
+    }
+    unsigned long long incl = (unsigned long long)run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long tmp = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o)
+            incl += tmp;
+    }
+    const unsigned long long excl = incl - (unsigned long long)run;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int j = 4 * lane + m + 1;
+        if (j < 104)
+            cf.pre[j] = (1ull << (kQ - 1)) + ((excl + (unsigned long long)v[m]) << 17);
+    }
+    if (lane == 0)
+        cf.pre[0] = 1ull << (kQ - 1);
+    __syncwarp();
+}
+
+template <int TPL>
+__device__ void warp_iir_core(const CoefSmem &cf, int order, int32_t *buf, int n)
 {
     const int lane = lane_id();
-    const long long half = 1ll << (kQ - 1);
-    long long cj[4];
+    uint32_t cl[TPL];
+    int32_t ch[TPL];
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        int j = lane + 1 + 32 * t;
-        cj[t] = (j <= order) ? sm.c[j] : 0;
+    for (int m = 0; m < TPL; m++) {
+        const int j = TPL * lane + m; // tap j+1
+        cl[m] = j < 112 ? cf.clo[j] : 0u;
+        ch[m] = j < 112 ? cf.chi[j] : 0;
     }
-    for (int i = 1; i < n; i++) {
-        long long part = 0;
+    unsigned long long alo[TPL];
+    uint32_t ahi[TPL];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int j = lane + 1 + 32 * t;
-            if (j <= order && j <= i)
-                part += cj[t] * (long long)buf[i - j];
-        }
-        unsigned long long tot = warp_sum_u64((unsigned long long)part);
-        if (lane == 0) {
-            long long acc = half - (long long)tot;
-            buf[i] = buf[i] - (int32_t)(acc >> kQ);
-        }
-        __syncwarp();
+    for (int m = 0; m < TPL; m++) {
+        alo[m] = 0;
+        ahi[m] = 0;
     }
+    const unsigned long long steady = cf.pre[order];
+    uint32_t sp = (uint32_t)(buf[0] + kSampleBias); // s[0] = r[0]
+    // step(u, i, base): consumes s'[i] in `sp`, produces s[i+1].  Slot m of this step
+    // lives in physical register (m + u) % TPL, so the per-step slot shift is free.
+#define SELAB200_IIR_STEP(u, i, base)                                                              \
+    {                                                                                              \
+        _Pragma("unroll") for (int m = 0; m < TPL; m++)                                            \
+        {                                                                                          \
+            alo[(m + (u)) % TPL] += (unsigned long long)cl[m] * sp;                                \
+            ahi[(m + (u)) % TPL] += (uint32_t)ch[m] * sp;                                          \
+        }                                                                                          \
+        const unsigned long long full0 = alo[(u) % TPL] + ((unsigned long long)ahi[(u) % TPL] << 32); \
+        unsigned long long incoming = __shfl_down_sync(kFull, full0, 1);                           \
+        if (lane == 31)                                                                            \
+            incoming = 0;                                                                          \
+        const unsigned long long tt = (base) - full0;                                              \
+        int vnext = buf[(i) + 1] - (int32_t)((long long)tt >> kQ);                                 \
+        vnext = __shfl_sync(kFull, vnext, 0);                                                      \
+        if (lane == 0)                                                                             \
+            buf[(i) + 1] = vnext;                                                                  \
+        alo[(u) % TPL] = incoming; /* becomes the top slot of the next step */                     \
+        ahi[(u) % TPL] = 0;                                                                        \
+        sp = (uint32_t)(vnext + kSampleBias);                                                      \
+    }
+    int i = 0;
+    const int last = n - 1; // steps i = 0 .. last-1
+    // warm-up: outputs 1..order use the prefix table
+    const int warm = order < last ? order : last;
+    const int warm_groups = (warm + TPL - 1) / TPL;
+    for (int gq = 0; gq < warm_groups; gq++) {
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            if (i < last) {
+                const int t = i + 1;
+                const unsigned long long base = cf.pre[t < order ? t : order];
+                SELAB200_IIR_STEP(u, i, base);
+                i++;
+            }
+        }
+    }
+    // steady state
+    for (; i + TPL <= last;) {
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            SELAB200_IIR_STEP(u, i, steady);
+            i++;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+        if (i < last) {
+            SELAB200_IIR_STEP(u, i, steady);
+            i++;
+        }
+    }
+#undef SELAB200_IIR_STEP
+    __syncwarp();
+}
+
+// buf: r on entry, s on exit (in place), n samples.
+__device__ void warp_iir_synthesis(CoefSmem &cf, int order, int32_t *buf, int n)
+{
+    warp_iir_prepare(cf, order);
+    if (order <= 32)
+        warp_iir_core<1>(cf, order, buf, n);
+    else if (order <= 64)
+        warp_iir_core<2>(cf, order, buf, n);
+    else
+        warp_iir_core<4>(cf, order, buf, n);
 }
 
 } // namespace selab200

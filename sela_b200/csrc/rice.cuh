@@ -134,36 +134,59 @@ __device__ void warp_rice_pack(const Val &val, int n, uint32_t k, uint32_t words
 
 // rice::RiceDecoder (src/rice/rice_decoder.cpp:11-52), ONE LANE PER STREAM: the parse
 // is inherently sequential, so the parallelism is across streams (subframes) and
-// every lane runs the tight scalar parser on its own stream.  Reads beyond n_words
-// see zero bits (bounded, unlike the reference).  Returns false if the stream ran
-// out of words before `count` symbols were complete.
+// every lane runs the tight scalar parser on its own stream.  The words are fetched
+// 16 bytes at a time, one vector ahead of use, so the dependent chain never waits on
+// memory; decoded values leave as 16-byte stores.  Reads beyond n_words see zero
+// bits (bounded, unlike the reference).  `src` must be readable up to the next
+// 16-byte boundary past its last word.  Returns false if the stream ran out of
+// words before `count` symbols were complete.
 __device__ bool lane_rice_decode(const uint32_t *__restrict__ src, uint32_t n_words, uint32_t k,
                                  uint32_t count, int32_t *__restrict__ out)
 {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+    const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    const uint32_t total = n_words + skip; // words counted from the aligned base
+    const uint32_t nvec = (total + 3) >> 2;
+    uint32_t vi = 2, wpos = skip;
+    uint4 cur = nvec > 0 ? __ldg(vp) : make_uint4(0, 0, 0, 0);
+    uint4 nxt = nvec > 1 ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
+    auto next_word = [&]() -> uint32_t {
+        const uint32_t sel = wpos & 3u;
+        uint32_t w = sel == 0 ? cur.x : sel == 1 ? cur.y : sel == 2 ? cur.z : cur.w;
+        if (wpos >= total)
+            w = 0;
+        wpos++;
+        if ((wpos & 3u) == 0) {
+            cur = nxt;
+            nxt = vi < nvec ? __ldg(vp + vi) : make_uint4(0, 0, 0, 0);
+            vi++;
+        }
+        return w;
+    };
+
     unsigned long long buf = 0;
-    uint32_t avail = 0, widx = 0;
+    uint32_t avail = 0;
     unsigned long long consumed = 0;
     auto refill = [&]() {
         if (avail <= 32) {
-            uint32_t w = widx < n_words ? __ldg(src + widx) : 0u;
-            widx++;
-            buf |= (unsigned long long)w << avail;
+            buf |= (unsigned long long)next_word() << avail;
             avail += 32;
         }
     };
+    const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    int32_t o0 = 0, o1 = 0, o2 = 0;
     refill();
     for (uint32_t i = 0; i < count; i++) {
         uint32_t q = 0;
         while (true) {
             const uint32_t inv = ~(uint32_t)buf;
-            if (inv == 0) { // 32 more ones
+            if (inv == 0) { // 32 more ones (never past the end: zero bits follow the last word)
                 q += 32;
                 buf >>= 32;
                 avail -= 32;
                 consumed += 32;
                 refill();
-                if (widx > n_words + 2)
-                    break; // past the end: zero bits follow, terminate
                 continue;
             }
             const uint32_t ones = __ffs(inv) - 1;
@@ -180,7 +203,22 @@ __device__ bool lane_rice_decode(const uint32_t *__restrict__ src, uint32_t n_wo
         consumed += k;
         refill();
         const uint32_t u = (q << k) | payload; // uint32 shift as in rice_decoder.cpp:37
-        out[i] = unzigzag(u);
+        const int32_t v = unzigzag(u);
+        if (vec_out) {
+            const uint32_t sel = i & 3u;
+            if (sel == 0) o0 = v;
+            else if (sel == 1) o1 = v;
+            else if (sel == 2) o2 = v;
+            else *reinterpret_cast<int4 *>(out + i - 3) = make_int4(o0, o1, o2, v);
+        } else {
+            out[i] = v;
+        }
+    }
+    if (vec_out) {
+        const uint32_t rem = count & 3u, b = count - rem;
+        if (rem > 0) out[b] = o0;
+        if (rem > 1) out[b + 1] = o1;
+        if (rem > 2) out[b + 2] = o2;
     }
     return consumed <= (unsigned long long)n_words * 32;
 }

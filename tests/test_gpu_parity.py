@@ -19,8 +19,13 @@ def O():
     return ol.best()
 
 
-def _analyse_all(O, frames):
-    return [O.lpc_analyse(s) for s in frames]
+def test_device_selftest_scaling():
+    import ctypes as C
+    from sela_b200 import _lib
+    _lib.init(0)
+    bad = C.c_uint32(123)
+    _lib.check(_lib.lib().selab200_selftest(C.addressof(bad)))
+    assert bad.value == 0
 
 
 def test_lpc_residues_families(O):

@@ -51,7 +51,9 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms from before the warm-up; only samples whose timestamp falls
+    inside the timed region [t0, t1] are kept."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -59,14 +61,16 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -77,16 +81,23 @@ class ClockSampler:
         os.unlink(self.f.name)
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        total = 0
         for r in rows:
             try:
-                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                vals = (float(r[1]), float(r[2]), float(r[3]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[3:7]):
+            total += 1
+            if not (t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
+            sm.append(vals[0]); smax.append(vals[1]); power.append(vals[2])
+            for n, v in zip(names, r[4:8]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "samples_total": total,
+                "reasons": sorted(reasons)}
 
 
 def make_pcm(seed):
@@ -184,6 +195,7 @@ def run_ours(args, rank, world, local_rank):
         codec.encode(pcm)
         codec.decode(out, n_words)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -191,8 +203,8 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     launches0 = L.selab200_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize()
+    t_wall0 = time.time()
     ev[0].record()
     for i in range(args.steps):
         codec.encode(pcm)
@@ -200,9 +212,10 @@ def run_ours(args, rank, world, local_rank):
         codec.decode(out, n_words)
         ev[2 * i + 2].record()
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     if dist:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     launches = L.selab200_launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     enc_ms = statistics.fmean(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
@@ -273,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms_max, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_encode<stereo> (fused analysis+FIR+Rice)", "bound": "hbm",
+            "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": enc_bytes,
@@ -296,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

@@ -120,8 +120,8 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     if (n_frames == 0)
         return 0;
     const bool stereo = channels == 2;
-    const size_t n_units = stereo ? n_frames : (size_t)n_frames * channels;
-    CUDA_TRY(cudaMemsetAsync(d_ws, 0, 256 + n_units * 8, stream));
+    const size_t n_units = encode_units(n_frames, channels);
+    const size_t n_sub = (size_t)n_frames * channels;
     EncodeParams p;
     p.pcm = d_pcm;
     p.n_frames = n_frames;
@@ -131,20 +131,26 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     p.capacity = capacity;
     p.words_used = reinterpret_cast<unsigned long long *>(d_used);
     p.status = d_status;
-    p.ticket = reinterpret_cast<uint32_t *>(d_ws);
-    p.scan = reinterpret_cast<unsigned long long *>(static_cast<char *>(d_ws) + 256);
+    p.units = static_cast<UnitRecord *>(d_ws);
+    p.slots = reinterpret_cast<uint32_t *>(static_cast<char *>(d_ws) + align256(n_units * sizeof(UnitRecord)));
     if (stereo) {
         constexpr size_t smem = encode_smem_bytes<true>();
-        if (int rc = set_smem(k_encode<true>, smem))
+        if (int rc = set_smem(k_encode_units<true>, smem))
             return rc;
-        k_encode<true><<<(unsigned)n_units, 96, smem, stream>>>(p);
+        k_encode_units<true><<<(unsigned)n_units, 32, smem, stream>>>(p);
     } else {
         constexpr size_t smem = encode_smem_bytes<false>();
-        if (int rc = set_smem(k_encode<false>, smem))
+        if (int rc = set_smem(k_encode_units<false>, smem))
             return rc;
-        k_encode<false><<<(unsigned)n_units, 32, smem, stream>>>(p);
+        k_encode_units<false><<<(unsigned)n_units, 32, smem, stream>>>(p);
     }
-    return launch_check("k_encode");
+    if (int rc = launch_check("k_encode_units"))
+        return rc;
+    k_encode_scan<<<1, 1024, 0, stream>>>(p);
+    if (int rc = launch_check("k_encode_scan"))
+        return rc;
+    k_encode_gather<<<(unsigned)((n_sub + 7) / 8), 256, 0, stream>>>(p);
+    return launch_check("k_encode_gather");
 }
 
 int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
@@ -169,17 +175,17 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     p.status = d_status;
     p.ws_q = static_cast<int32_t *>(d_ws);
     p.ws_res = reinterpret_cast<int32_t *>(static_cast<char *>(d_ws) + align256(n_sub * 128 * 4));
-    const unsigned blocks = (unsigned)((n_sub + 127) / 128);
-    k_rice_decode<<<blocks, 128, 0, stream>>>(p, 0);
+    const unsigned blocks = (unsigned)((n_sub + 32 * kRiceWarps - 1) / (32 * kRiceWarps));
+    k_rice_decode<<<blocks, 32 * kRiceWarps, 0, stream>>>(p, 0);
     if (int rc = launch_check("k_rice_decode(refl)"))
         return rc;
-    k_rice_decode<<<blocks, 128, 0, stream>>>(p, 1);
+    k_rice_decode<<<blocks, 32 * kRiceWarps, 0, stream>>>(p, 1);
     if (int rc = launch_check("k_rice_decode(res)"))
         return rc;
     const size_t smem = synthesise_smem_bytes(channels);
     if (int rc = set_smem(k_synthesise, smem))
         return rc;
-    k_synthesise<<<n_frames, 32 * channels, smem, stream>>>(p);
+    k_synthesise<<<n_frames, 32 * ((channels + 1) / 2), smem, stream>>>(p);
     return launch_check("k_synthesise");
 }
 
@@ -267,14 +273,15 @@ void selab200_host_free(void *p)
 
 size_t selab200_encode_words_bound(uint32_t n_frames, uint32_t channels)
 {
-    // residues: <= 2048*(1 + 19) + sum(u >> 19) bits with |r| < 2^21 for in-domain audio,
-    // i.e. < 2048*24 bits = 1536 words; reflection coefficients: <= 100*(8+1) bits.
-    return (size_t)n_frames * channels * (1536 + 32) + 64;
+    // A subframe never exceeds its scratch slot (larger streams are refused with
+    // SELAB200_ERR_RANGE): residues <= 1568 words (24.5 bits/sample), coefficients <= 32.
+    return (size_t)n_frames * channels * kSlotWords + 64;
 }
 
 size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 {
-    return 256 + (size_t)n_frames * channels * 8 + 256;
+    const size_t n_units = encode_units(n_frames, channels);
+    return align256(n_units * sizeof(UnitRecord)) + n_units * (size_t)kSlotWords * 4 + 256;
 }
 
 size_t selab200_decode_workspace_bytes(uint32_t n_frames, uint32_t channels)
@@ -522,7 +529,7 @@ int selab200_rice_decode(const uint32_t *words, const uint32_t *n_words, uint32_
     CUDA_TRY(cudaMemcpyAsync(d_nw, n_words, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaMemcpyAsync(d_k, rice_param, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaMemcpyAsync(d_counts, counts, (size_t)n_streams * 4, cudaMemcpyHostToDevice, g.stream));
-    k_rice_decode_streams<<<(n_streams + 127) / 128, 128, 0, g.stream>>>(
+    k_rice_decode_streams<<<(n_streams + 32 * kRiceWarps - 1) / (32 * kRiceWarps), 32 * kRiceWarps, 0, g.stream>>>(
         static_cast<const uint32_t *>(g.words.ptr), d_nw, words_stride, d_k, d_counts, n_streams,
         static_cast<int32_t *>(g.work.ptr), out_stride, d_status);
     if (int rc = launch_check("k_rice_decode_streams"))

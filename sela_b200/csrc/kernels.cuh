@@ -17,6 +17,28 @@
 namespace selab200 {
 
 // ------------------------------------------------------------------ encode --
+//
+// Three launches, no inter-CTA dependency anywhere:
+//   k_encode_units   one WARP per analysis unit (a channel, or for stereo the three
+//                    candidates ch0 / ch1 / ch0-ch1 of a frame): PCM -> autocorrelation ->
+//                    Schur -> quantise -> step-up -> FIR -> Rice parameter search -> Rice
+//                    pack into the unit's private slot of a scratch arena + a 32-byte
+//                    unit record.  No barriers, no atomics between units.
+//   k_encode_scan    one CTA: stereo decision (difference wins iff strictly fewer words,
+//                    src/frame/frame_encoder.cpp:63-72), exclusive prefix sum of the chosen
+//                    sizes in file order, descriptors, total.
+//   k_encode_gather  one warp per emitted subframe: slot -> final arena offset.
+
+constexpr uint32_t kSlotWords = 1600;     // per-unit scratch slot (refl words first, then residue words)
+constexpr uint32_t kSlotReflWords = 32;   // 100 coefficients * (8 + 1) bits <= 29 words
+
+struct UnitRecord {                       // 32 bytes
+    uint32_t order;
+    uint32_t refl_k, refl_words;
+    uint32_t res_k, res_words;
+    uint32_t flags;                       // 1 = too large for the slot / the uint16 fields
+    uint32_t pad[2];
+};
 
 struct EncodeParams {
     const int16_t *pcm;            // [n_frames][2048][channels] interleaved
@@ -26,127 +48,59 @@ struct EncodeParams {
     unsigned long long capacity;   // words
     unsigned long long *words_used;
     int32_t *status;
-    uint32_t *ticket;              // workspace: dynamic unit counter
-    unsigned long long *scan;      // workspace: [n_units] look-back state
+    UnitRecord *units;             // workspace [n_units]
+    uint32_t *slots;               // workspace [n_units][kSlotWords]
 };
 
-struct SubframeResult {
-    uint32_t order;
-    RiceChoice refl, res;
-};
-
-// flag in the two top bits of a scan entry
-constexpr unsigned long long kScanAggregate = 1ull << 62;
-constexpr unsigned long long kScanPrefix    = 2ull << 62;
-constexpr unsigned long long kScanValueMask = (1ull << 62) - 1;
-
-// Exclusive prefix of the unit sizes (decoupled look-back, single thread).
-// Units take tickets in increasing order, so every predecessor is resident or done.
-__device__ unsigned long long scan_exclusive(unsigned long long *scan, uint32_t unit, unsigned long long agg)
+__host__ __device__ inline uint32_t encode_units(uint32_t n_frames, uint32_t channels)
 {
-    volatile unsigned long long *vs = scan;
-    if (unit == 0) {
-        vs[0] = kScanPrefix | agg;
-        __threadfence();
-        return 0;
-    }
-    vs[unit] = kScanAggregate | agg;
-    __threadfence();
-    unsigned long long sum = 0;
-    uint32_t p = unit - 1;
-    while (true) {
-        unsigned long long v = vs[p];
-        if ((v >> 62) == 0)
-            continue; // predecessor has not published yet
-        sum += v & kScanValueMask;
-        if (v & kScanPrefix)
-            break;
-        p--;
-    }
-    vs[unit] = kScanPrefix | (sum + agg);
-    __threadfence();
-    return sum;
-}
-
-__device__ __forceinline__ void write_desc(selab200_subframe_desc *d, uint32_t channel, uint32_t type,
-                                           uint32_t parent, const SubframeResult &r,
-                                           unsigned long long refl_off)
-{
-    selab200_subframe_desc v;
-    v.channel = (uint8_t)channel;
-    v.subframe_type = (uint8_t)type;
-    v.parent_channel = (uint8_t)parent;
-    v.refl_rice_param = (uint8_t)r.refl.k;
-    v.refl_words = (uint16_t)r.refl.words;
-    v.lpc_order = (uint8_t)r.order;
-    v.res_rice_param = (uint8_t)r.res.k;
-    v.res_words = (uint16_t)r.res.words;
-    v.samples = (uint16_t)kFrame;
-    v.reserved = 0;
-    v.refl_offset = refl_off;
-    v.res_offset = refl_off + r.refl.words;
-    *d = v;
+    return channels == 2 ? n_frames * 3u : n_frames * channels;
 }
 
 template <bool STEREO>
-__global__ void __launch_bounds__(STEREO ? 96 : 32) k_encode(EncodeParams p)
+__global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
 {
-    constexpr int kWarps = STEREO ? 3 : 1;
-    constexpr int kChan = STEREO ? 2 : 1; // channels held in shared memory per CTA
     constexpr int kRow = kHistoryPad + kFrame;
+    constexpr int kChan = STEREO ? 2 : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                        // [kChan][pad + 2048]
-    WarpScratch *scratch_all = reinterpret_cast<WarpScratch *>(smem_raw + kChan * kRow * 2);
-    CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(scratch_all + kWarps);
-    SubframeResult *results = reinterpret_cast<SubframeResult *>(coef_all + kWarps);
-    unsigned long long *base_slot = reinterpret_cast<unsigned long long *>(results + 4);
-    uint32_t *unit_slot = reinterpret_cast<uint32_t *>(base_slot + 1);
+    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                    // [kChan][pad + 2048]
+    WarpScratch &scratch = *reinterpret_cast<WarpScratch *>(smem_raw + kChan * kRow * 2);
+    CoefSmem &cf = *reinterpret_cast<CoefSmem *>(smem_raw + kChan * kRow * 2 + sizeof(WarpScratch));
 
-    const int warp = warp_id(), lane = lane_id();
-    if (threadIdx.x == 0)
-        *unit_slot = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t unit = *unit_slot;
-    const uint32_t n_units = STEREO ? p.n_frames : p.n_frames * p.channels;
-    if (unit >= n_units)
-        return;
-    const uint32_t frame = STEREO ? unit : unit / p.channels;
-    const uint32_t chan0 = STEREO ? 0 : unit % p.channels;
+    const int lane = lane_id();
+    const uint32_t unit = blockIdx.x;
+    const uint32_t frame = STEREO ? unit / 3 : unit / p.channels;
+    const uint32_t role = STEREO ? unit % 3 : unit % p.channels; // stereo: 0 ch0, 1 ch1, 2 ch0-ch1
 
-    // ---- stage the PCM of this unit (de-interleave to planar int16, zero history in front) ----
+    // ---- stage the PCM (de-interleave to planar int16, zero history in front) ----
     const int16_t *src = p.pcm + (size_t)frame * kFrame * p.channels;
-    for (int j = threadIdx.x; j < kChan * kHistoryPad / 2; j += blockDim.x) {
+    for (int j = lane; j < kChan * kHistoryPad / 2; j += 32) {
         const int c = j / (kHistoryPad / 2), o = j % (kHistoryPad / 2);
         reinterpret_cast<uint32_t *>(s16 + c * kRow)[o] = 0;
     }
-    int16_t *ch0 = s16 + kHistoryPad;
+    int16_t *row0 = s16 + kHistoryPad;
+    Signal sig;
     if (STEREO) {
-        int16_t *ch1 = ch0 + kRow;
+        int16_t *row1 = row0 + kRow;
         const uint4 *src128 = reinterpret_cast<const uint4 *>(src); // 4 stereo sample pairs per load
-        for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) {
+        for (int j = lane; j < kFrame / 4; j += 32) {
             const uint4 v = src128[j];
             const uint32_t l0 = __byte_perm(v.x, v.y, 0x5410), r0 = __byte_perm(v.x, v.y, 0x7632);
             const uint32_t l1 = __byte_perm(v.z, v.w, 0x5410), r1 = __byte_perm(v.z, v.w, 0x7632);
-            reinterpret_cast<uint2 *>(ch0)[j] = make_uint2(l0, l1);
-            reinterpret_cast<uint2 *>(ch1)[j] = make_uint2(r0, r1);
+            reinterpret_cast<uint2 *>(row0)[j] = make_uint2(l0, l1);
+            reinterpret_cast<uint2 *>(row1)[j] = make_uint2(r0, r1);
         }
+        sig.a = (role == 1) ? row1 : row0;
+        sig.b = (role == 2) ? row1 : nullptr;
     } else {
-        for (int j = threadIdx.x; j < kFrame; j += blockDim.x)
-            ch0[j] = src[(size_t)j * p.channels + chan0];
-    }
-    __syncthreads();
-
-    // ---- per-warp analysis ----
-    Signal sig;
-    if (STEREO) {
-        sig.a = (warp == 1) ? ch0 + kRow : ch0;
-        sig.b = (warp == 2) ? ch0 + kRow : nullptr;
-    } else {
-        sig.a = ch0;
+        for (int j = lane; j < kFrame; j += 32)
+            row0[j] = src[(size_t)j * p.channels + role];
+        sig.a = row0;
         sig.b = nullptr;
     }
-    WarpScratch &scratch = scratch_all[warp];
-    CoefSmem &cf = coef_all[warp];
+    __syncwarp();
+
+    // ---- analysis ----
     int32_t *res = scratch.res;
     warp_autocorrelation(sig, scratch.a);
     warp_schur(scratch.a);
@@ -154,73 +108,136 @@ __global__ void __launch_bounds__(STEREO ? 96 : 32) k_encode(EncodeParams p)
     warp_coefficients(cf, scratch.a.t, order);
     warp_fir_residual(sig, cf, order, res);
 
+    // ---- Rice: parameter search, then pack into this unit's slot ----
     const int32_t *qv = cf.q;
     auto q_at = [qv](int i) { return qv[i]; };
     auto r_at = [res](int i) { return res[i]; };
-    SubframeResult mine;
-    mine.order = order;
-    mine.refl = warp_rice_choose(q_at, order);
-    mine.res = warp_rice_choose(r_at, kFrame);
-    if (lane == 0)
-        results[warp] = mine;
-    __syncthreads();
-
-    // ---- stereo decision + arena offset ----
-    bool emit = true;
-    uint32_t channel = chan0, type = 0, parent = chan0;
-    unsigned long long my_off = 0, unit_words;
-    if (STEREO) {
-        const unsigned long long w0 = (unsigned long long)results[0].refl.words + results[0].res.words;
-        const unsigned long long wa = (unsigned long long)results[1].refl.words + results[1].res.words;
-        const unsigned long long wd = (unsigned long long)results[2].refl.words + results[2].res.words;
-        const bool diff_wins = wd < wa; // strictly smaller (src/frame/frame_encoder.cpp:63-72)
-        unit_words = w0 + (diff_wins ? wd : wa);
-        if (warp == 0) {
-            channel = 0; parent = 0;
-        } else {
-            emit = (warp == 2) == diff_wins;
-            channel = 1;
-            type = diff_wins ? 1 : 0;
-            parent = diff_wins ? 0 : 1;
-            my_off = w0;
-        }
-    } else {
-        unit_words = (unsigned long long)mine.refl.words + mine.res.words;
+    const RiceChoice cq = warp_rice_choose(q_at, order);
+    const RiceChoice cr = warp_rice_choose(r_at, kFrame);
+    const bool too_large = cq.words > kSlotReflWords || cr.words > kSlotWords - kSlotReflWords;
+    uint32_t *slot = p.slots + (size_t)unit * kSlotWords;
+    if (!too_large) {
+        warp_rice_pack(q_at, order, cq.k, cq.words, slot);
+        warp_rice_pack(r_at, kFrame, cr.k, cr.words, slot + kSlotReflWords);
     }
-    if (threadIdx.x == 0) {
-        *base_slot = scan_exclusive(p.scan, unit, unit_words);
-        if (unit == n_units - 1)
-            *p.words_used = *base_slot + unit_words;
+    if (lane == 0) {
+        UnitRecord u;
+        u.order = order;
+        u.refl_k = cq.k;
+        u.refl_words = cq.words;
+        u.res_k = cr.k;
+        u.res_words = cr.words;
+        u.flags = too_large ? 1u : 0u;
+        u.pad[0] = u.pad[1] = 0;
+        p.units[unit] = u;
     }
-    __syncthreads();
-    const unsigned long long base = *base_slot + my_off;
-
-    if (!emit)
-        return;
-    if (mine.refl.words > 0xffffu || mine.res.words > 0xffffu) {
-        // the uint16 word-count fields cannot hold this (the reference would truncate)
-        if (lane == 0)
-            raise_status(p.status, SELAB200_ERR_RANGE);
-        return;
-    }
-    if (*base_slot + unit_words > p.capacity) {
-        if (lane == 0)
-            raise_status(p.status, SELAB200_ERR_CAPACITY);
-        return;
-    }
-    warp_rice_pack(q_at, order, mine.refl.k, mine.refl.words, p.words + base);
-    warp_rice_pack(r_at, kFrame, mine.res.k, mine.res.words, p.words + base + mine.refl.words);
-    if (lane == 0)
-        write_desc(p.descs + (size_t)frame * p.channels + channel, channel, type, parent, mine, base);
 }
 
 template <bool STEREO>
 constexpr size_t encode_smem_bytes()
 {
-    constexpr int kWarps = STEREO ? 3 : 1;
-    constexpr int kChan = STEREO ? 2 : 1;
-    return (size_t)kChan * (kHistoryPad + kFrame) * 2 + kWarps * (sizeof(WarpScratch) + sizeof(CoefSmem)) +
-           4 * sizeof(SubframeResult) + 16;
+    return (size_t)(STEREO ? 2 : 1) * (kHistoryPad + kFrame) * 2 + sizeof(WarpScratch) + sizeof(CoefSmem);
+}
+
+// Which unit is emitted for output subframe (frame, channel), and as what.
+struct Emit {
+    uint32_t unit, type, parent;
+};
+__device__ __forceinline__ Emit choose_unit(const UnitRecord *units, uint32_t channels, uint32_t sub)
+{
+    Emit e;
+    if (channels != 2) {
+        e.unit = sub;
+        e.type = 0;
+        e.parent = sub % channels;
+        return e;
+    }
+    const uint32_t frame = sub >> 1;
+    if ((sub & 1) == 0) {
+        e.unit = 3 * frame;
+        e.type = 0;
+        e.parent = 0;
+        return e;
+    }
+    const UnitRecord a = units[3 * frame + 1], d = units[3 * frame + 2];
+    const bool diff_wins = (unsigned long long)d.refl_words + d.res_words <
+                           (unsigned long long)a.refl_words + a.res_words; // strictly smaller
+    e.unit = 3 * frame + (diff_wins ? 2 : 1);
+    e.type = diff_wins ? 1 : 0;
+    e.parent = diff_wins ? 0 : 1;
+    return e;
+}
+
+__global__ void __launch_bounds__(1024) k_encode_scan(EncodeParams p)
+{
+    __shared__ unsigned long long partial[1024];
+    const uint32_t n_sub = p.n_frames * p.channels;
+    const uint32_t per = (n_sub + 1023) / 1024;
+    const uint32_t lo = min(threadIdx.x * per, n_sub), hi = min(lo + per, n_sub);
+    unsigned long long sum = 0;
+    bool bad = false;
+    for (uint32_t sub = lo; sub < hi; sub++) {
+        const Emit e = choose_unit(p.units, p.channels, sub);
+        const UnitRecord u = p.units[e.unit];
+        sum += (unsigned long long)u.refl_words + u.res_words;
+        bad |= u.flags != 0 || u.refl_words > 0xffffu || u.res_words > 0xffffu;
+    }
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = threadIdx.x >= o ? partial[threadIdx.x - o] : 0;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long off = partial[threadIdx.x] - sum;
+    if (threadIdx.x == 1023) {
+        *p.words_used = partial[1023];
+        if (partial[1023] > p.capacity)
+            raise_status(p.status, SELAB200_ERR_CAPACITY);
+    }
+    if (bad)
+        raise_status(p.status, SELAB200_ERR_RANGE); // a stream the uint16 word counts cannot describe
+    for (uint32_t sub = lo; sub < hi; sub++) {
+        const Emit e = choose_unit(p.units, p.channels, sub);
+        const UnitRecord u = p.units[e.unit];
+        selab200_subframe_desc v;
+        v.channel = (uint8_t)(sub % p.channels);
+        v.subframe_type = (uint8_t)e.type;
+        v.parent_channel = (uint8_t)e.parent;
+        v.refl_rice_param = (uint8_t)u.refl_k;
+        v.refl_words = (uint16_t)u.refl_words;
+        v.lpc_order = (uint8_t)u.order;
+        v.res_rice_param = (uint8_t)u.res_k;
+        v.res_words = (uint16_t)u.res_words;
+        v.samples = (uint16_t)kFrame;
+        v.reserved = 0;
+        v.refl_offset = off;
+        v.res_offset = off + u.refl_words;
+        p.descs[sub] = v;
+        off += (unsigned long long)u.refl_words + u.res_words;
+    }
+}
+
+// One warp per emitted subframe; 8 warps per CTA.
+__global__ void __launch_bounds__(256) k_encode_gather(EncodeParams p)
+{
+    const uint32_t sub = blockIdx.x * 8 + warp_id();
+    const uint32_t n_sub = p.n_frames * p.channels;
+    if (sub >= n_sub || *reinterpret_cast<volatile int32_t *>(p.status) != 0)
+        return;
+    const int lane = lane_id();
+    const Emit e = choose_unit(p.units, p.channels, sub);
+    const selab200_subframe_desc d = p.descs[sub];
+    const uint32_t *slot = p.slots + (size_t)e.unit * kSlotWords;
+    uint32_t *dst = p.words + d.refl_offset;
+    for (uint32_t w = lane; w < d.refl_words; w += 32)
+        dst[w] = slot[w];
+    dst = p.words + d.res_offset;
+    slot += kSlotReflWords;
+    for (uint32_t w = lane; w < d.res_words; w += 32)
+        dst[w] = slot[w];
 }
 
 // ------------------------------------------------------------------ decode --
@@ -246,38 +263,51 @@ struct DecodeParams {
     int32_t *ws_res; // [n_sub][2048]
 };
 
-// K5: one lane per stream.  which = 0: reflection streams, 1: residue streams.
-__global__ void __launch_bounds__(128) k_rice_decode(DecodeParams p, int which)
+// K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams, 1: residue streams.
+constexpr int kRiceWarps = 2;
+__global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p, int which)
 {
+    __shared__ uint32_t ring[kRiceWarps][kRiceRingWords * 32];
     const uint32_t sub = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_sub = p.n_frames * p.channels;
-    if (sub >= n_sub)
-        return;
-    const selab200_subframe_desc d = p.descs[sub];
-    if (!desc_ok(d, p.channels, p.n_words)) {
-        raise_status(p.status, SELAB200_ERR_BITSTREAM);
-        return;
+    RiceLaneStream st;
+    st.src = p.words;
+    st.n_words = 0;
+    st.k = 0;
+    st.count = 0;
+    st.out = nullptr;
+    if (sub < n_sub) {
+        const selab200_subframe_desc d = p.descs[sub];
+        if (!desc_ok(d, p.channels, p.n_words)) {
+            raise_status(p.status, SELAB200_ERR_BITSTREAM);
+        } else if (which == 0) {
+            st.src = p.words + d.refl_offset;
+            st.n_words = d.refl_words;
+            st.k = d.refl_rice_param;
+            st.count = d.lpc_order;
+            st.out = p.ws_q + (size_t)sub * 128;
+        } else {
+            st.src = p.words + d.res_offset;
+            st.n_words = d.res_words;
+            st.k = d.res_rice_param;
+            st.count = d.samples;
+            st.out = p.ws_res + (size_t)sub * kFrame;
+        }
     }
-    bool ok;
-    if (which == 0)
-        ok = lane_rice_decode(p.words + d.refl_offset, d.refl_words, d.refl_rice_param, d.lpc_order,
-                              p.ws_q + (size_t)sub * 128);
-    else
-        ok = lane_rice_decode(p.words + d.res_offset, d.res_words, d.res_rice_param, d.samples,
-                              p.ws_res + (size_t)sub * kFrame);
-    if (!ok)
+    if (!warp_rice_decode32(ring[warp_id()], st))
         raise_status(p.status, SELAB200_ERR_BITSTREAM);
 }
 
-// K6: CTA per frame, warp per subframe.
+// K6: CTA per frame; each warp synthesises TWO subframes (one per half-warp).
 __global__ void k_synthesise(DecodeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t ch = p.channels;
     int32_t *planes = reinterpret_cast<int32_t *>(smem_raw);                  // [ch][2048], by channel
     CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(planes + (size_t)ch * kFrame);
-    double *t_all = reinterpret_cast<double *>(coef_all + ch);                // [ch][104]
-    int *meta = reinterpret_cast<int *>(t_all + (size_t)ch * 104); // [ch] type, [ch] parent, [1] valid
+    double *t_all = reinterpret_cast<double *>(coef_all + ch);                // [warps][104]
+    const uint32_t n_warps = (ch + 1) / 2;
+    int *meta = reinterpret_cast<int *>(t_all + (size_t)n_warps * 104); // [ch] type, [ch] parent, [1] valid
 
     const uint32_t frame = blockIdx.x;
     const int warp = warp_id(), lane = lane_id();
@@ -313,20 +343,32 @@ __global__ void k_synthesise(DecodeParams p)
     }
 
     {
-        const uint32_t sub = frame * ch + warp;
-        const selab200_subframe_desc d = fd[warp];
-        CoefSmem &cf = coef_all[warp];
-        int32_t *buf = planes + (size_t)d.channel * kFrame;
-        const int order = d.lpc_order;
-        for (int i = lane; i < 104; i += 32)
-            cf.q[i] = i < order ? p.ws_q[(size_t)sub * 128 + i] : 0;
-        const int32_t *r = p.ws_res + (size_t)sub * kFrame;
-        for (int i = lane; i < kFrame; i += 32)
-            buf[i] = r[i];
-        __syncwarp();
-        // order 0 behaves like order 1 with a zero predictor (linear_predictor.cpp:19-22)
-        warp_coefficients(cf, t_all + warp * 104, order);
-        warp_iir_synthesis(cf, order, buf, kFrame);
+        // positions 2*warp (half A) and 2*warp+1 (half B); an odd channel count leaves the
+        // last half idle: it shadows half A without storing
+        const uint32_t pos_a = 2 * warp, pos_b = 2 * warp + 1;
+        const bool has_b = pos_b < ch;
+        for (uint32_t h = 0; h < (has_b ? 2u : 1u); h++) {
+            const uint32_t pos = h ? pos_b : pos_a;
+            const uint32_t sub = frame * ch + pos;
+            const selab200_subframe_desc d = fd[pos];
+            CoefSmem &cf = coef_all[pos];
+            int32_t *buf = planes + (size_t)d.channel * kFrame;
+            const int order = d.lpc_order;
+            for (int i = lane; i < 104; i += 32)
+                cf.q[i] = i < order ? p.ws_q[(size_t)sub * 128 + i] : 0;
+            const int4 *r4 = reinterpret_cast<const int4 *>(p.ws_res + (size_t)sub * kFrame);
+            for (int i = lane; i < kFrame / 4; i += 32)
+                reinterpret_cast<int4 *>(buf)[i] = r4[i];
+            __syncwarp();
+            // order 0 behaves like order 1 with a zero predictor (linear_predictor.cpp:19-22)
+            warp_coefficients(cf, t_all + warp * 104, order);
+            warp_iir_prepare(cf, order);
+        }
+        const bool upper = lane >= 16;
+        const uint32_t my_pos = (upper && has_b) ? pos_b : pos_a;
+        const selab200_subframe_desc d = fd[my_pos];
+        warp_iir_synthesis_pair(coef_all[my_pos], d.lpc_order, planes + (size_t)d.channel * kFrame,
+                                !upper || has_b, kFrame);
     }
     __syncthreads();
 
@@ -342,7 +384,8 @@ __global__ void k_synthesise(DecodeParams p)
 
 inline size_t synthesise_smem_bytes(uint32_t ch)
 {
-    return (size_t)ch * kFrame * 4 + ch * (sizeof(CoefSmem) + 104 * sizeof(double)) + (2 * ch + 1) * sizeof(int);
+    return (size_t)ch * kFrame * 4 + ch * sizeof(CoefSmem) + ((ch + 1) / 2) * 104 * sizeof(double) +
+           (2 * ch + 1) * sizeof(int);
 }
 
 // ------------------------------------------------------------ stage level --
@@ -394,7 +437,8 @@ __global__ void __launch_bounds__(32) k_lpc_samples(const int32_t *residues, uin
         buf[i] = residues[(size_t)sub * kFrame + i];
     __syncwarp();
     warp_coefficients(cf, t, order);
-    warp_iir_synthesis(cf, order, buf, kFrame);
+    warp_iir_prepare(cf, order);
+    warp_iir_synthesis_pair(cf, order, buf, lane < 16, kFrame); // upper half shadows, never stores
     for (int i = lane; i < kFrame; i += 32)
         samples[(size_t)sub * kFrame + i] = buf[i];
 }
@@ -432,20 +476,30 @@ __global__ void __launch_bounds__(32) k_rice_encode(const int32_t *values, const
 }
 
 // rice::RiceDecoder::process, one stream per lane.
-__global__ void __launch_bounds__(128) k_rice_decode_streams(const uint32_t *words, const uint32_t *n_words,
-                                                             uint32_t words_stride, const uint32_t *k,
-                                                             const uint32_t *counts, uint32_t n_streams,
-                                                             int32_t *out, uint32_t out_stride, int32_t *status)
+__global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
+    const uint32_t *words, const uint32_t *n_words, uint32_t words_stride, const uint32_t *k,
+    const uint32_t *counts, uint32_t n_streams, int32_t *out, uint32_t out_stride, int32_t *status)
 {
-    const uint32_t st = blockIdx.x * blockDim.x + threadIdx.x;
-    if (st >= n_streams)
-        return;
-    if (k[st] >= 32 || counts[st] > out_stride || n_words[st] > words_stride) {
-        raise_status(status, SELAB200_ERR_BITSTREAM);
-        return;
+    __shared__ uint32_t ring[kRiceWarps][kRiceRingWords * 32];
+    const uint32_t st_i = blockIdx.x * blockDim.x + threadIdx.x;
+    RiceLaneStream st;
+    st.src = words;
+    st.n_words = 0;
+    st.k = 0;
+    st.count = 0;
+    st.out = nullptr;
+    if (st_i < n_streams) {
+        if (k[st_i] >= 32 || counts[st_i] > out_stride || n_words[st_i] > words_stride) {
+            raise_status(status, SELAB200_ERR_BITSTREAM);
+        } else {
+            st.src = words + (size_t)st_i * words_stride;
+            st.n_words = n_words[st_i];
+            st.k = k[st_i];
+            st.count = counts[st_i];
+            st.out = out + (size_t)st_i * out_stride;
+        }
     }
-    lane_rice_decode(words + (size_t)st * words_stride, n_words[st], k[st], counts[st],
-                     out + (size_t)st * out_stride);
+    warp_rice_decode32(ring[warp_id()], st);
 }
 
 } // namespace selab200

@@ -426,53 +426,54 @@ __device__ void warp_iir_prepare(CoefSmem &cf, int order)
     __syncwarp();
 }
 
+// Two subframes share a warp: lanes 0-15 run subframe A, lanes 16-31 subframe B, each
+// lane owning TPL taps (TPL*15 >= order, so the last lane of a half only ever holds
+// zero coefficients and its accumulators stay zero -- shfl_down past the half's edge
+// returns the lane's own, zero, value: no special case).  Per step the warp issues
+// 2*TPL IMADs + ~14 bookkeeping instructions for TWO samples.
 template <int TPL>
-__device__ void warp_iir_core(const CoefSmem &cf, int order, int32_t *buf, int n)
+__device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool active, int n, int order_max)
 {
-    const int lane = lane_id();
+    const int hl = lane_id() & 15;
     uint32_t cl[TPL];
     int32_t ch[TPL];
 #pragma unroll
     for (int m = 0; m < TPL; m++) {
-        const int j = TPL * lane + m; // tap j+1
+        const int j = TPL * hl + m; // tap j+1
         cl[m] = j < 112 ? cf.clo[j] : 0u;
         ch[m] = j < 112 ? cf.chi[j] : 0;
     }
-    unsigned long long alo[TPL];
-    uint32_t ahi[TPL];
+    unsigned long long acc[TPL];
 #pragma unroll
-    for (int m = 0; m < TPL; m++) {
-        alo[m] = 0;
-        ahi[m] = 0;
-    }
+    for (int m = 0; m < TPL; m++)
+        acc[m] = 0;
     const unsigned long long steady = cf.pre[order];
     uint32_t sp = (uint32_t)(buf[0] + kSampleBias); // s[0] = r[0]
+    const bool writer = active && hl == 0;
     // step(u, i, base): consumes s'[i] in `sp`, produces s[i+1].  Slot m of this step
     // lives in physical register (m + u) % TPL, so the per-step slot shift is free.
-#define SELAB200_IIR_STEP(u, i, base)                                                              \
-    {                                                                                              \
-        _Pragma("unroll") for (int m = 0; m < TPL; m++)                                            \
-        {                                                                                          \
-            alo[(m + (u)) % TPL] += (unsigned long long)cl[m] * sp;                                \
-            ahi[(m + (u)) % TPL] += (uint32_t)ch[m] * sp;                                          \
-        }                                                                                          \
-        const unsigned long long full0 = alo[(u) % TPL] + ((unsigned long long)ahi[(u) % TPL] << 32); \
-        unsigned long long incoming = __shfl_down_sync(kFull, full0, 1);                           \
-        if (lane == 31)                                                                            \
-            incoming = 0;                                                                          \
-        const unsigned long long tt = (base) - full0;                                              \
-        int vnext = buf[(i) + 1] - (int32_t)((long long)tt >> kQ);                                 \
-        vnext = __shfl_sync(kFull, vnext, 0);                                                      \
-        if (lane == 0)                                                                             \
-            buf[(i) + 1] = vnext;                                                                  \
-        alo[(u) % TPL] = incoming; /* becomes the top slot of the next step */                     \
-        ahi[(u) % TPL] = 0;                                                                        \
-        sp = (uint32_t)(vnext + kSampleBias);                                                      \
+#define SELAB200_IIR_STEP(u, i, base)                                                            \
+    {                                                                                            \
+        _Pragma("unroll") for (int m = 0; m < TPL; m++)                                          \
+        {                                                                                        \
+            unsigned long long &a_ = acc[(m + (u)) % TPL];                                       \
+            a_ += (unsigned long long)cl[m] * sp;                                                \
+            a_ += (unsigned long long)((uint32_t)ch[m] * sp) << 32;                              \
+        }                                                                                        \
+        const unsigned long long full0 = acc[(u) % TPL];                                         \
+        const unsigned long long incoming = __shfl_down_sync(kFull, full0, 1, 16);               \
+        const unsigned long long tt = (base) - full0;                                            \
+        int vnext = buf[(i) + 1] - (int32_t)((long long)tt >> kQ);                               \
+        vnext = __shfl_sync(kFull, vnext, 0, 16);                                                \
+        if (writer)                                                                              \
+            buf[(i) + 1] = vnext;                                                                \
+        acc[(u) % TPL] = incoming; /* becomes the top slot of the next step */                   \
+        sp = (uint32_t)(vnext + kSampleBias);                                                    \
     }
     int i = 0;
     const int last = n - 1; // steps i = 0 .. last-1
-    // warm-up: outputs 1..order use the prefix table
-    const int warm = order < last ? order : last;
+    // warm-up: outputs 1..order use the prefix table (the longer of the two orders decides)
+    const int warm = order_max < last ? order_max : last;
     const int warm_groups = (warm + TPL - 1) / TPL;
     for (int gq = 0; gq < warm_groups; gq++) {
 #pragma unroll
@@ -504,16 +505,19 @@ __device__ void warp_iir_core(const CoefSmem &cf, int order, int32_t *buf, int n
     __syncwarp();
 }
 
-// buf: r on entry, s on exit (in place), n samples.
-__device__ void warp_iir_synthesis(CoefSmem &cf, int order, int32_t *buf, int n)
+// Synthesis of two subframes in one warp.  cf/buf/order/active are PER HALF (lanes
+// 0-15: A, lanes 16-31: B); cf.pre must be ready (warp_iir_prepare).  buf: r on entry,
+// s on exit (in place), n samples.  An inactive half computes but never stores.
+__device__ void warp_iir_synthesis_pair(const CoefSmem &cf, int order, int32_t *buf, bool active, int n)
 {
-    warp_iir_prepare(cf, order);
-    if (order <= 32)
-        warp_iir_core<1>(cf, order, buf, n);
-    else if (order <= 64)
-        warp_iir_core<2>(cf, order, buf, n);
+    const int other = __shfl_xor_sync(kFull, order, 16);
+    const int order_max = order > other ? order : other;
+    if (order_max <= 30)
+        warp_iir_pair<2>(cf, order, buf, active, n, order_max);
+    else if (order_max <= 60)
+        warp_iir_pair<4>(cf, order, buf, active, n, order_max);
     else
-        warp_iir_core<4>(cf, order, buf, n);
+        warp_iir_pair<8>(cf, order, buf, active, n, order_max);
 }
 
 } // namespace selab200

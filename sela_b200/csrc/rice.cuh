@@ -133,94 +133,104 @@ __device__ void warp_rice_pack(const Val &val, int n, uint32_t k, uint32_t words
 }
 
 // rice::RiceDecoder (src/rice/rice_decoder.cpp:11-52), ONE LANE PER STREAM: the parse
-// is inherently sequential, so the parallelism is across streams (subframes) and
-// every lane runs the tight scalar parser on its own stream.  The words are fetched
-// 16 bytes at a time, one vector ahead of use, so the dependent chain never waits on
-// memory; decoded values leave as 16-byte stores.  Reads beyond n_words see zero
-// bits (bounded, unlike the reference).  `src` must be readable up to the next
-// 16-byte boundary past its last word.  Returns false if the stream ran out of
-// words before `count` symbols were complete.
-__device__ bool lane_rice_decode(const uint32_t *__restrict__ src, uint32_t n_words, uint32_t k,
-                                 uint32_t count, int32_t *__restrict__ out)
-{
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
-    const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
-    const uint4 *vp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
-    const uint32_t total = n_words + skip; // words counted from the aligned base
-    const uint32_t nvec = (total + 3) >> 2;
-    uint32_t vi = 2, wpos = skip;
-    uint4 cur = nvec > 0 ? __ldg(vp) : make_uint4(0, 0, 0, 0);
-    uint4 nxt = nvec > 1 ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
-    auto next_word = [&]() -> uint32_t {
-        const uint32_t sel = wpos & 3u;
-        uint32_t w = sel == 0 ? cur.x : sel == 1 ? cur.y : sel == 2 ? cur.z : cur.w;
-        if (wpos >= total)
-            w = 0;
-        wpos++;
-        if ((wpos & 3u) == 0) {
-            cur = nxt;
-            nxt = vi < nvec ? __ldg(vp + vi) : make_uint4(0, 0, 0, 0);
-            vi++;
-        }
-        return w;
-    };
+// is inherently sequential, so the parallelism is across streams (subframes); the 32
+// lanes of a warp run the same branch-free scalar parser on 32 different streams.
+//
+// Words reach the parsers through a per-warp shared-memory ring: ring[w & 127][lane]
+// holds word w of lane's stream (bank = lane for every parser read).  The ring is
+// filled COOPERATIVELY, 64 words (two coalesced 128-byte loads by the whole warp) of
+// one stream at a time, whenever a lane is within three words of its loaded range --
+// so global memory only ever sees coalesced loads, and the parser's dependent chain is
+// LDS -> funnel shift -> ffs -> LDS -> funnel shift -> brev.
+// Reads beyond n_words see zero bits (bounded, unlike the reference).
+struct RiceLaneStream {
+    const uint32_t *src;
+    uint32_t n_words, k, count;
+    int32_t *out;
+};
+constexpr int kRiceRingWords = 128; // per lane; ring is [128][32] uint32 = 16 KB per warp
 
-    unsigned long long buf = 0;
-    uint32_t avail = 0;
-    unsigned long long consumed = 0;
-    auto refill = [&]() {
-        if (avail <= 32) {
-            buf |= (unsigned long long)next_word() << avail;
-            avail += 32;
-        }
+// Returns (per lane) false if the stream needed more bits than n_words holds.
+__device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
+{
+    const int lane = lane_id();
+    uint32_t next_block = 0; // per lane: next 64-word block of MY stream to load
+    auto load_block = [&](int owner) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(
+            shfl_u64(reinterpret_cast<unsigned long long>(st.src), owner));
+        const uint32_t nw = __shfl_sync(kFull, st.n_words, owner);
+        const uint32_t nb = __shfl_sync(kFull, next_block, owner);
+        const uint32_t w0 = nb * 64 + lane, w1 = w0 + 32;
+        const uint32_t v0 = w0 < nw ? __ldg(src + w0) : 0u;
+        const uint32_t v1 = w1 < nw ? __ldg(src + w1) : 0u;
+        ring[(w0 & 127) * 32 + owner] = v0; // column write: 32-way bank conflict, off the parsers' path
+        ring[(w1 & 127) * 32 + owner] = v1;
+        if (lane == owner)
+            next_block++;
     };
-    const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int owner = 0; owner < 32; owner++) {
+        load_block(owner);
+        load_block(owner);
+    }
+    __syncwarp();
+
+    uint32_t pos = 0, i = 0, q_acc = 0;
+    const uint32_t k = st.k;
+    bool done = st.count == 0;
+    const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
     int32_t o0 = 0, o1 = 0, o2 = 0;
-    refill();
-    for (uint32_t i = 0; i < count; i++) {
-        uint32_t q = 0;
-        while (true) {
-            const uint32_t inv = ~(uint32_t)buf;
-            if (inv == 0) { // 32 more ones (never past the end: zero bits follow the last word)
-                q += 32;
-                buf >>= 32;
-                avail -= 32;
-                consumed += 32;
-                refill();
-                continue;
+    while (__ballot_sync(kFull, !done)) {
+        // refill: the block holding word (pos>>5)+3 must be resident
+        unsigned need = __ballot_sync(kFull, !done && ((((pos >> 5) + 3) >> 6) >= next_block));
+        if (need) {
+            __syncwarp();
+            while (need) {
+                const int owner = __ffs(need) - 1;
+                need &= need - 1;
+                load_block(owner);
             }
-            const uint32_t ones = __ffs(inv) - 1;
-            q += ones;
-            buf >>= ones + 1;
-            avail -= ones + 1;
-            consumed += ones + 1;
-            break;
+            __syncwarp();
         }
-        refill();
-        const uint32_t payload = k ? (__brev((uint32_t)buf) >> (32 - k)) : 0u;
-        buf >>= k;
-        avail -= k;
-        consumed += k;
-        refill();
-        const uint32_t u = (q << k) | payload; // uint32 shift as in rice_decoder.cpp:37
-        const int32_t v = unzigzag(u);
-        if (vec_out) {
-            const uint32_t sel = i & 3u;
-            if (sel == 0) o0 = v;
-            else if (sel == 1) o1 = v;
-            else if (sel == 2) o2 = v;
-            else *reinterpret_cast<int4 *>(out + i - 3) = make_int4(o0, o1, o2, v);
-        } else {
-            out[i] = v;
+        if (!done) {
+            const uint32_t wi = pos >> 5;
+            const uint32_t a0 = ring[(wi & 127) * 32 + lane], a1 = ring[((wi + 1) & 127) * 32 + lane];
+            const uint32_t inv = ~__funnelshift_r(a0, a1, pos);
+            const bool run = inv == 0;                  // 32 more ones, no terminator yet
+            const uint32_t ones = run ? 32u : (uint32_t)(__ffs(inv) - 1);
+            const uint32_t q = q_acc + ones;
+            const uint32_t p2 = pos + ones + (run ? 0u : 1u);
+            const uint32_t wj = p2 >> 5;
+            const uint32_t b0 = ring[(wj & 127) * 32 + lane], b1 = ring[((wj + 1) & 127) * 32 + lane];
+            const uint32_t win = __funnelshift_r(b0, b1, p2);
+            const uint32_t payload = k ? (__brev(win) >> (32 - k)) : 0u;
+            if (run) {
+                q_acc = q;
+                pos = p2;
+            } else {
+                const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
+                q_acc = 0;
+                pos = p2 + k;
+                if (vec_out) {
+                    const uint32_t sel = i & 3u;
+                    if (sel == 0) o0 = v;
+                    else if (sel == 1) o1 = v;
+                    else if (sel == 2) o2 = v;
+                    else *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
+                } else {
+                    st.out[i] = v;
+                }
+                i++;
+                done = i == st.count;
+            }
         }
     }
-    if (vec_out) {
-        const uint32_t rem = count & 3u, b = count - rem;
-        if (rem > 0) out[b] = o0;
-        if (rem > 1) out[b + 1] = o1;
-        if (rem > 2) out[b + 2] = o2;
+    if (vec_out && st.count) {
+        const uint32_t rem = st.count & 3u, b = st.count - rem;
+        if (rem > 0) st.out[b] = o0;
+        if (rem > 1) st.out[b + 1] = o1;
+        if (rem > 2) st.out[b + 2] = o2;
     }
-    return consumed <= (unsigned long long)n_words * 32;
+    return pos <= st.n_words * 32u;
 }
 
 } // namespace selab200

@@ -47,6 +47,16 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
     return __shfl_sync(kFull, v, src);
 }
 
+// d = a*b + c with a 32x32->64 multiply (IMAD.WIDE.U32).  Spelled in PTX because NVVM
+// likes to hoist the zero-extension of a loop-invariant operand into a 64-bit register,
+// after which ptxas emits a full 64x32 multiply (an extra IMAD + IADD per tap).
+__device__ __forceinline__ unsigned long long mad_wide_u32(uint32_t a, uint32_t b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 {
 #pragma unroll

@@ -363,7 +363,7 @@ __device__ void warp_fir_residual(const Sig &sig, const CoefSmem &cf, int order,
                 for (int r = 0; r < 8; r++) {
                     const int idx = 7 + r - tau; // window position of s[i0 + r - (8t + 1 + tau)]
                     const uint32_t w = idx < 8 ? lo[idx] : hi[idx - 8];
-                    alo[r] += (unsigned long long)cl[tau] * w;
+                    alo[r] = mad_wide_u32(cl[tau], w, alo[r]);
                     ahi[r] += (uint32_t)ch[tau] * w;
                 }
             }
@@ -443,10 +443,15 @@ __device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool 
         cl[m] = j < 112 ? cf.clo[j] : 0u;
         ch[m] = j < 112 ? cf.chi[j] : 0;
     }
-    unsigned long long acc[TPL];
+    // accumulators: 64-bit low-word products + a separate 32-bit column for the high-word
+    // products (one IMAD.WIDE.U32 + one IMAD per tap); combined only when handed on
+    unsigned long long alo[TPL];
+    uint32_t ahi[TPL];
 #pragma unroll
-    for (int m = 0; m < TPL; m++)
-        acc[m] = 0;
+    for (int m = 0; m < TPL; m++) {
+        alo[m] = 0;
+        ahi[m] = 0;
+    }
     const unsigned long long steady = cf.pre[order];
     uint32_t sp = (uint32_t)(buf[0] + kSampleBias); // s[0] = r[0]
     const bool writer = active && hl == 0;
@@ -456,18 +461,18 @@ __device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool 
     {                                                                                            \
         _Pragma("unroll") for (int m = 0; m < TPL; m++)                                          \
         {                                                                                        \
-            unsigned long long &a_ = acc[(m + (u)) % TPL];                                       \
-            a_ += (unsigned long long)cl[m] * sp;                                                \
-            a_ += (unsigned long long)((uint32_t)ch[m] * sp) << 32;                              \
+            alo[(m + (u)) % TPL] = mad_wide_u32(cl[m], sp, alo[(m + (u)) % TPL]);               \
+            ahi[(m + (u)) % TPL] += (uint32_t)ch[m] * sp;                                        \
         }                                                                                        \
-        const unsigned long long full0 = acc[(u) % TPL];                                         \
+        const unsigned long long full0 = alo[(u) % TPL] + ((unsigned long long)ahi[(u) % TPL] << 32); \
         const unsigned long long incoming = __shfl_down_sync(kFull, full0, 1, 16);               \
         const unsigned long long tt = (base) - full0;                                            \
         int vnext = buf[(i) + 1] - (int32_t)((long long)tt >> kQ);                               \
         vnext = __shfl_sync(kFull, vnext, 0, 16);                                                \
         if (writer)                                                                              \
             buf[(i) + 1] = vnext;                                                                \
-        acc[(u) % TPL] = incoming; /* becomes the top slot of the next step */                   \
+        alo[(u) % TPL] = incoming; /* becomes the top slot of the next step */                   \
+        ahi[(u) % TPL] = 0;                                                                      \
         sp = (uint32_t)(vnext + kSampleBias);                                                    \
     }
     int i = 0;

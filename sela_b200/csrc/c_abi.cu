@@ -62,13 +62,43 @@ struct DeviceBuffer {
     }
 };
 
+constexpr int kMaxChunks = 64;
+
 struct Context {
     bool ready = false;
     int device = -1;
-    cudaStream_t stream = nullptr;
-    DeviceBuffer in, descs, words, work, aux, small;
-    int32_t *h_small = nullptr; // pinned: [0] status, [2..3] words_used
+    cudaStream_t stream = nullptr;                 // stage-level calls
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined batch calls: copy engines ...
+    cudaStream_t s_compute[2] = {nullptr, nullptr}; // ... and two alternating compute lanes
+    cudaEvent_t ev_h2d[kMaxChunks], ev_done[kMaxChunks], ev_scan[kMaxChunks], ev_reset;
+    bool events = false;
+    DeviceBuffer in, descs, words, work, work2, aux, small;
+    int32_t *h_small = nullptr;                    // pinned: [0] status, [2..3] words_used
+    unsigned long long *h_totals = nullptr;        // pinned: arena fill level after each chunk
 } g;
+
+// On every exit from a pipelined call -- error paths included -- nothing may still be
+// reading or writing the caller's host buffers.
+struct PipelineDrain {
+    ~PipelineDrain()
+    {
+        for (cudaStream_t st : {g.s_h2d, g.s_compute[0], g.s_compute[1], g.s_d2h})
+            if (st)
+                cudaStreamSynchronize(st);
+    }
+};
+
+// Chunking of the pipelined host-buffer calls: enough chunks to overlap PCIe with compute,
+// each still several waves of warps, workspace bounded for huge batches.
+uint32_t chunk_frames_for(uint32_t n_frames)
+{
+    uint32_t c = (n_frames + 7) / 8;
+    if (c < 512) c = 512;
+    if (c > 16384) c = 16384;
+    while ((n_frames + c - 1) / c > (uint32_t)kMaxChunks)
+        c *= 2;
+    return c;
+}
 
 const char *status_text(int s)
 {
@@ -107,16 +137,22 @@ int launch_check(const char *what)
 
 // ---- device-resident cores (no synchronisation) --------------------------
 
+// `fresh`: reset status and the arena fill level first (a stand-alone batch); the pipelined
+// host path resets once and then chains chunks through *d_used.  `before_scan`: optional event
+// the scan must wait for (the previous chunk's scan, when chunks alternate between streams).
 int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *d_descs,
                   uint32_t *d_words, size_t capacity, uint64_t *d_used, int32_t *d_status, void *d_ws,
-                  size_t ws_bytes, cudaStream_t stream)
+                  size_t ws_bytes, cudaStream_t stream, bool fresh = true, cudaEvent_t before_scan = nullptr,
+                  cudaEvent_t after_scan = nullptr)
 {
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     if (ws_bytes < selab200_encode_workspace_bytes(n_frames, channels))
         return fail(SELAB200_ERR_ARGUMENT, "encode workspace too small");
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
-    CUDA_TRY(cudaMemsetAsync(d_used, 0, sizeof(uint64_t), stream));
+    if (fresh) {
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+        CUDA_TRY(cudaMemsetAsync(d_used, 0, sizeof(uint64_t), stream));
+    }
     if (n_frames == 0)
         return 0;
     const bool stereo = channels == 2;
@@ -146,22 +182,27 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     }
     if (int rc = launch_check("k_encode_units"))
         return rc;
+    if (before_scan)
+        CUDA_TRY(cudaStreamWaitEvent(stream, before_scan, 0));
     k_encode_scan<<<1, 1024, 0, stream>>>(p);
     if (int rc = launch_check("k_encode_scan"))
         return rc;
+    if (after_scan)
+        CUDA_TRY(cudaEventRecord(after_scan, stream));
     k_encode_gather<<<(unsigned)((n_sub + 7) / 8), 256, 0, stream>>>(p);
     return launch_check("k_encode_gather");
 }
 
 int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
                   const uint32_t *d_words, size_t n_words, int16_t *d_pcm, int32_t *d_status, void *d_ws,
-                  size_t ws_bytes, cudaStream_t stream)
+                  size_t ws_bytes, cudaStream_t stream, bool fresh = true)
 {
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     if (ws_bytes < selab200_decode_workspace_bytes(n_frames, channels))
         return fail(SELAB200_ERR_ARGUMENT, "decode workspace too small");
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+    if (fresh)
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
     if (n_frames == 0)
         return 0;
     const size_t n_sub = (size_t)n_frames * channels;
@@ -224,10 +265,26 @@ int selab200_init(int device)
     if (prop.major < 10)
         return fail(SELAB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
                     prop.major, prop.minor);
-    if (!g.stream)
+    if (!g.stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[0], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[1], cudaStreamNonBlocking));
+    }
+    if (!g.events) {
+        for (int i = 0; i < kMaxChunks; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_scan[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
+        g.events = true;
+    }
     if (!g.h_small)
         CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_small), 64));
+    if (!g.h_totals)
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_totals), (kMaxChunks + 1) * 8));
     if (int rc = g.small.ensure(256))
         return rc;
     g.device = device;
@@ -245,13 +302,28 @@ void selab200_shutdown(void)
     g.descs.release();
     g.words.release();
     g.work.release();
+    g.work2.release();
     g.aux.release();
     g.small.release();
     if (g.h_small)
         cudaFreeHost(g.h_small);
     g.h_small = nullptr;
-    cudaStreamDestroy(g.stream);
-    g.stream = nullptr;
+    if (g.h_totals)
+        cudaFreeHost(g.h_totals);
+    g.h_totals = nullptr;
+    for (cudaStream_t st : {g.stream, g.s_h2d, g.s_d2h, g.s_compute[0], g.s_compute[1]})
+        if (st)
+            cudaStreamDestroy(st);
+    g.stream = g.s_h2d = g.s_d2h = g.s_compute[0] = g.s_compute[1] = nullptr;
+    if (g.events)
+        for (int i = 0; i < kMaxChunks; i++) {
+            cudaEventDestroy(g.ev_h2d[i]);
+            cudaEventDestroy(g.ev_done[i]);
+            cudaEventDestroy(g.ev_scan[i]);
+        }
+    if (g.events)
+        cudaEventDestroy(g.ev_reset);
+    g.events = false;
     g.ready = false;
 }
 
@@ -317,6 +389,14 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
                          workspace_bytes, (cudaStream_t)stream);
 }
 
+// Host-buffer batch calls.  Pipelined in chunks of frames over three engines:
+//   s_h2d      PCM (encode) / descriptors + words (decode) of chunk c+1 .. go up
+//   s_compute  two alternating lanes run the kernels of chunk c (tails of one chunk overlap the
+//              head of the next; the encoder's scans are chained by events because each needs
+//              the arena fill level its predecessor left in *d_used)
+//   s_d2h      results of chunk c-1 come down
+// With pinned host buffers (selab200_host_alloc) the three overlap; pageable memory works
+// but serialises inside the driver.
 int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
                            selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
                            size_t *words_used)
@@ -326,37 +406,68 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
         return rc;
     if (!pcm || !descs || !words || !words_used)
         return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     *words_used = 0;
     if (n_frames == 0)
         return 0;
+    PipelineDrain drain;
+    const uint32_t cf = chunk_frames_for(n_frames);
+    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
     const size_t n_sub = (size_t)n_frames * channels;
-    const size_t pcm_bytes = n_sub * kFrame * 2;
-    const size_t ws_bytes = selab200_encode_workspace_bytes(n_frames, channels);
-    if (int rc = g.in.ensure(pcm_bytes)) return rc;
+    const size_t frame_bytes = (size_t)channels * kFrame * 2;
+    const size_t ws_bytes = selab200_encode_workspace_bytes(cf, channels);
+    if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(words_capacity * 4 + 16)) return rc;
     if (int rc = g.work.ensure(ws_bytes)) return rc;
+    if (int rc = g.work2.ensure(n_chunks > 1 ? ws_bytes : 0)) return rc;
     int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
     uint64_t *d_used = reinterpret_cast<uint64_t *>(static_cast<char *>(g.small.ptr) + 8);
-    CUDA_TRY(cudaMemcpyAsync(g.in.ptr, pcm, pcm_bytes, cudaMemcpyHostToDevice, g.stream));
-    if (int rc = encode_device(static_cast<const int16_t *>(g.in.ptr), n_frames, channels,
-                               static_cast<selab200_subframe_desc *>(g.descs.ptr),
-                               static_cast<uint32_t *>(g.words.ptr), words_capacity, d_used, d_status, g.work.ptr,
-                               g.work.bytes, g.stream))
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(g.h_small, g.small.ptr, 16, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(descs, g.descs.ptr, n_sub * sizeof(selab200_subframe_desc), cudaMemcpyDeviceToHost,
-                             g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
+    selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
+    uint32_t *d_words = static_cast<uint32_t *>(g.words.ptr);
+
+    CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
+    CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
+    CUDA_TRY(cudaStreamWaitEvent(g.s_compute[1], g.ev_reset, 0));
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        CUDA_TRY(cudaMemcpyAsync(d_pcm + (size_t)f0 * channels * kFrame, pcm + (size_t)f0 * channels * kFrame,
+                                 nf * frame_bytes, cudaMemcpyHostToDevice, g.s_h2d));
+        CUDA_TRY(cudaEventRecord(g.ev_h2d[c], g.s_h2d));
+        cudaStream_t cs = g.s_compute[c & 1];
+        DeviceBuffer &ws = (c & 1) ? g.work2 : g.work;
+        CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
+        if (int rc = encode_device(d_pcm + (size_t)f0 * channels * kFrame, nf, channels, d_descs + (size_t)f0 * channels,
+                                   d_words, words_capacity, d_used, d_status, ws.ptr, ws.bytes, cs, false,
+                                   c ? g.ev_scan[c - 1] : nullptr, g.ev_scan[c]))
+            return rc;
+        // fill level after this chunk -> host (ordered after this chunk's scan; tiny)
+        CUDA_TRY(cudaMemcpyAsync(&g.h_totals[c + 1], d_used, 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
+    }
+    g.h_totals[0] = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        CUDA_TRY(cudaEventSynchronize(g.ev_done[c]));
+        const unsigned long long lo = g.h_totals[c], hi = g.h_totals[c + 1];
+        if (hi > words_capacity || hi < lo)
+            break; // capacity exceeded: reported through the status word below
+        CUDA_TRY(cudaMemcpyAsync(descs + (size_t)f0 * channels, d_descs + (size_t)f0 * channels,
+                                 (size_t)nf * channels * sizeof(selab200_subframe_desc), cudaMemcpyDeviceToHost,
+                                 g.s_d2h));
+        CUDA_TRY(cudaMemcpyAsync(words + lo, d_words + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(g.s_compute[0]));
+    CUDA_TRY(cudaStreamSynchronize(g.s_compute[1]));
+    CUDA_TRY(cudaMemcpyAsync(g.h_small, g.small.ptr, 16, cudaMemcpyDeviceToHost, g.s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(g.s_d2h));
     uint64_t used;
     memcpy(&used, g.h_small + 2, 8);
-    if (g.h_small[0] != 0) {
-        *words_used = (size_t)used; // for CAPACITY: the size the caller needs
+    *words_used = (size_t)used; // for CAPACITY: the size the caller needs
+    if (g.h_small[0] != 0)
         return fail(g.h_small[0], "%s", status_text(g.h_small[0]));
-    }
-    CUDA_TRY(cudaMemcpyAsync(words, g.words.ptr, used * 4, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
-    *words_used = (size_t)used;
     return 0;
 }
 
@@ -368,25 +479,61 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
         return rc;
     if (!descs || !pcm_out || (!words && n_words))
         return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     if (n_frames == 0)
         return 0;
+    PipelineDrain drain;
+    const uint32_t cf = chunk_frames_for(n_frames);
+    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
     const size_t n_sub = (size_t)n_frames * channels;
-    const size_t pcm_bytes = n_sub * kFrame * 2;
-    const size_t ws_bytes = selab200_decode_workspace_bytes(n_frames, channels);
-    if (int rc = g.in.ensure(pcm_bytes)) return rc;
+    const size_t frame_bytes = (size_t)channels * kFrame * 2;
+    const size_t ws_bytes = selab200_decode_workspace_bytes(cf, channels);
+    if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(n_words * 4 + 16)) return rc;
     if (int rc = g.work.ensure(ws_bytes)) return rc;
+    if (int rc = g.work2.ensure(n_chunks > 1 ? ws_bytes : 0)) return rc;
     int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
-    CUDA_TRY(cudaMemcpyAsync(g.descs.ptr, descs, n_sub * sizeof(selab200_subframe_desc), cudaMemcpyHostToDevice,
-                             g.stream));
-    CUDA_TRY(cudaMemcpyAsync(g.words.ptr, words, n_words * 4, cudaMemcpyHostToDevice, g.stream));
-    if (int rc = decode_device(static_cast<const selab200_subframe_desc *>(g.descs.ptr), n_frames, channels,
-                               static_cast<const uint32_t *>(g.words.ptr), n_words,
-                               static_cast<int16_t *>(g.in.ptr), d_status, g.work.ptr, g.work.bytes, g.stream))
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(pcm_out, g.in.ptr, pcm_bytes, cudaMemcpyDeviceToHost, g.stream));
-    return read_status(g.stream, d_status);
+    int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
+    selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
+    uint32_t *d_words = static_cast<uint32_t *>(g.words.ptr);
+
+    CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
+    CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
+    CUDA_TRY(cudaStreamWaitEvent(g.s_compute[1], g.ev_reset, 0));
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        // the words this chunk's descriptors reference (descriptors need not be in arena order)
+        unsigned long long lo = ~0ull, hi = 0;
+        const selab200_subframe_desc *dc = descs + (size_t)f0 * channels;
+        for (size_t i = 0; i < (size_t)nf * channels; i++) {
+            const unsigned long long a0 = dc[i].refl_offset, a1 = a0 + dc[i].refl_words;
+            const unsigned long long b0 = dc[i].res_offset, b1 = b0 + dc[i].res_words;
+            if (a1 <= n_words && b1 <= n_words) { // out-of-range descriptors are rejected on the device
+                lo = a0 < lo ? a0 : lo;
+                lo = b0 < lo ? b0 : lo;
+                hi = a1 > hi ? a1 : hi;
+                hi = b1 > hi ? b1 : hi;
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_descs + (size_t)f0 * channels, dc, (size_t)nf * channels * sizeof(*dc),
+                                 cudaMemcpyHostToDevice, g.s_h2d));
+        if (hi > lo)
+            CUDA_TRY(cudaMemcpyAsync(d_words + lo, words + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, g.s_h2d));
+        CUDA_TRY(cudaEventRecord(g.ev_h2d[c], g.s_h2d));
+        cudaStream_t cs = g.s_compute[c & 1];
+        DeviceBuffer &ws = (c & 1) ? g.work2 : g.work;
+        CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
+        if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_words, n_words,
+                                   d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))
+            return rc;
+        CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
+        CUDA_TRY(cudaStreamWaitEvent(g.s_d2h, g.ev_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(pcm_out + (size_t)f0 * channels * kFrame, d_pcm + (size_t)f0 * channels * kFrame,
+                                 nf * frame_bytes, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    return read_status(g.s_d2h, d_status);
 }
 
 int selab200_selftest(uint32_t *mismatches)

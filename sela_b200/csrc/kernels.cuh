@@ -191,10 +191,14 @@ __global__ void __launch_bounds__(1024) k_encode_scan(EncodeParams p)
         partial[threadIdx.x] += v;
         __syncthreads();
     }
-    unsigned long long off = partial[threadIdx.x] - sum;
+    // *words_used is in/out: the arena fill level before this batch (0, or where the
+    // previous chunk of a pipelined call stopped) and after it
+    const unsigned long long base = *p.words_used;
+    __syncthreads();
+    unsigned long long off = base + partial[threadIdx.x] - sum;
     if (threadIdx.x == 1023) {
-        *p.words_used = partial[1023];
-        if (partial[1023] > p.capacity)
+        *p.words_used = base + partial[1023];
+        if (base + partial[1023] > p.capacity)
             raise_status(p.status, SELAB200_ERR_CAPACITY);
     }
     if (bad)

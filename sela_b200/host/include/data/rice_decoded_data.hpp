@@ -1,0 +1,3 @@
+// forwarding header: same include path as the reference tree
+#pragma once
+#include "../sela_types.hpp"

@@ -1,0 +1,631 @@
+// sela_host.cpp -- C++ mirror of the reference's operator interface over the CUDA C ABI.
+//
+// Host glue only (container parsing, value-struct <-> flat-buffer conversion); every
+// sample is analysed, filtered and coded on the GPU through include/sela_b200.h.
+// Device errors become `throw data::Exception(...)` (src/include/data/exception.hpp:7-14).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "sela_api.hpp"
+#include "../../../include/sela_b200.h"
+
+namespace {
+
+constexpr uint32_t kFrame = SELAB200_FRAME_SAMPLES;
+
+[[noreturn]] void raise(const std::string &what)
+{
+    throw data::Exception(std::string(what));
+}
+
+void check(int status)
+{
+    if (status != SELAB200_OK)
+        raise(std::string("sela_b200: ") + selab200_last_error());
+}
+
+void ensure_device()
+{
+    static bool ready = false;
+    if (ready)
+        return;
+    const char *env = std::getenv("SELAB200_DEVICE");
+    check(selab200_init(env ? std::atoi(env) : 0));
+    ready = true;
+}
+
+// Pinned staging buffer (RAII) for the batch calls.
+template <typename T>
+struct Pinned {
+    T *p = nullptr;
+    size_t n = 0;
+    explicit Pinned(size_t count) : n(count)
+    {
+        p = static_cast<T *>(selab200_host_alloc(std::max<size_t>(count, 1) * sizeof(T)));
+        if (!p)
+            raise("sela_b200: pinned host allocation failed");
+    }
+    ~Pinned() { selab200_host_free(p); }
+    Pinned(const Pinned &) = delete;
+    Pinned &operator=(const Pinned &) = delete;
+};
+
+int16_t narrow_sample(int32_t v)
+{
+    if (v < INT16_MIN || v > INT16_MAX)
+        raise("sela_b200: sample outside the 16-bit range (only 16-bit audio is supported)");
+    return (int16_t)v;
+}
+
+data::SelaFrame frame_from_descs(const selab200_subframe_desc *d, uint32_t channels, const uint32_t *words, uint8_t bits)
+{
+    data::SelaFrame out(bits);
+    out.subFrames.reserve(channels);
+    for (uint32_t c = 0; c < channels; c++) {
+        const selab200_subframe_desc &s = d[c];
+        data::RiceEncodedData refl(s.refl_rice_param, s.lpc_order,
+                                   std::vector<uint32_t>(words + s.refl_offset, words + s.refl_offset + s.refl_words));
+        data::RiceEncodedData res(s.res_rice_param, s.samples,
+                                  std::vector<uint32_t>(words + s.res_offset, words + s.res_offset + s.res_words));
+        out.subFrames.push_back(data::SelaSubFrame(s.channel, s.subframe_type, s.parent_channel, refl, res));
+    }
+    return out;
+}
+
+size_t frame_words(const data::SelaFrame &f)
+{
+    size_t n = 0;
+    for (const data::SelaSubFrame &s : f.subFrames)
+        n += s.encodedReflectionCoefficients.size() + s.encodedResidues.size();
+    return n;
+}
+
+void flatten_frame(const data::SelaFrame &f, selab200_subframe_desc *d, uint32_t *words, size_t &cursor)
+{
+    for (const data::SelaSubFrame &s : f.subFrames) {
+        std::memset(d, 0, sizeof *d);
+        d->channel = s.channel;
+        d->subframe_type = s.subFrameType;
+        d->parent_channel = s.parentChannelNumber;
+        d->refl_rice_param = s.reflectionCoefficientRiceParam;
+        d->refl_words = (uint16_t)s.encodedReflectionCoefficients.size();
+        d->lpc_order = s.optimumLpcOrder;
+        d->res_rice_param = s.residueRiceParam;
+        d->res_words = (uint16_t)s.encodedResidues.size();
+        d->samples = s.samplesPerChannel;
+        d->refl_offset = cursor;
+        std::copy(s.encodedReflectionCoefficients.begin(), s.encodedReflectionCoefficients.end(), words + cursor);
+        cursor += s.encodedReflectionCoefficients.size();
+        d->res_offset = cursor;
+        std::copy(s.encodedResidues.begin(), s.encodedResidues.end(), words + cursor);
+        cursor += s.encodedResidues.size();
+        d++;
+    }
+}
+
+// little-endian field readers over a byte buffer
+struct Bytes {
+    const std::vector<char> &b;
+    uint32_t u8(size_t o) const { return (uint8_t)b[o]; }
+    uint32_t u16(size_t o) const { return u8(o) | (u8(o + 1) << 8); }
+    uint32_t u32(size_t o) const { return u16(o) | (u16(o + 2) << 16); }
+    std::string tag(size_t o) const { return std::string(b.begin() + o, b.begin() + o + 4); }
+};
+
+std::vector<char> slurp(std::ifstream &in)
+{
+    std::vector<char> contents;
+    in.seekg(0, std::ios::end);
+    const std::streamoff size = in.tellg();
+    contents.resize(size > 0 ? (size_t)size : 0);
+    in.seekg(0, std::ios::beg);
+    if (!contents.empty())
+        in.read(contents.data(), (std::streamsize)contents.size());
+    return contents;
+}
+
+template <typename T>
+void put(std::ofstream &out, const T &v)
+{
+    out.write(reinterpret_cast<const char *>(&v), sizeof v);
+}
+
+} // namespace
+
+// ------------------------------------------------------------------- rice --
+
+namespace rice {
+
+RiceEncoder::RiceEncoder(const data::RiceDecodedData &decodedData) : input(decodedData.decodedData) {}
+
+// rice::RiceEncoder::process (src/rice/rice_encoder.cpp:73-81)
+data::RiceEncodedData RiceEncoder::process()
+{
+    ensure_device();
+    const uint32_t n = (uint32_t)input.size();
+    if (n > kFrame)
+        raise("sela_b200: rice::RiceEncoder handles at most 2048 values per stream");
+    uint32_t count = n, k = 0, n_words = 0;
+    const uint32_t stride = std::max<uint32_t>(n, 1);
+    std::vector<int32_t> values(stride, 0);
+    std::copy(input.begin(), input.end(), values.begin());
+    uint32_t cap = 2 * stride + 8;
+    std::vector<uint32_t> words(cap);
+    int rc = selab200_rice_encode(values.data(), &count, 1, stride, &k, &n_words, words.data(), cap);
+    if (rc == SELAB200_ERR_CAPACITY) { // rare: more than ~64 bits per value
+        cap = n_words;
+        words.assign(cap, 0);
+        rc = selab200_rice_encode(values.data(), &count, 1, stride, &k, &n_words, words.data(), cap);
+    }
+    check(rc);
+    words.resize(n_words);
+    return data::RiceEncodedData((int32_t)k, (int32_t)n, std::move(words));
+}
+
+RiceDecoder::RiceDecoder(const data::RiceEncodedData &encodedData)
+    : input(encodedData.encodedData), dataCount(encodedData.dataCount), optimumRiceParam(encodedData.optimumRiceParam)
+{
+}
+
+// rice::RiceDecoder::process (src/rice/rice_decoder.cpp:54-61)
+data::RiceDecodedData RiceDecoder::process()
+{
+    ensure_device();
+    uint32_t n_words = (uint32_t)input.size(), k = optimumRiceParam, count = dataCount;
+    std::vector<uint32_t> words(std::max<size_t>(input.size(), 1), 0);
+    std::copy(input.begin(), input.end(), words.begin());
+    std::vector<int32_t> out(std::max<uint32_t>(count, 1), 0);
+    check(selab200_rice_decode(words.data(), &n_words, (uint32_t)words.size(), &k, &count, 1, out.data(),
+                               (uint32_t)out.size()));
+    out.resize(count);
+    return data::RiceDecodedData(std::move(out));
+}
+
+} // namespace rice
+
+// -------------------------------------------------------------------- lpc --
+
+namespace lpc {
+
+ResidueGenerator::ResidueGenerator(const data::LpcDecodedData &data) : samples(data.samples), bitsPerSample(data.bitsPerSample) {}
+
+// lpc::ResidueGenerator::process (src/lpc/residue_generator.cpp:121-134)
+data::LpcEncodedData ResidueGenerator::process()
+{
+    ensure_device();
+    if (samples.size() != kFrame)
+        raise("sela_b200: lpc::ResidueGenerator needs exactly 2048 samples (the codec's frame size)");
+    uint8_t order = 0;
+    std::vector<int32_t> q(SELAB200_MAX_LPC_ORDER), res(kFrame);
+    check(selab200_lpc_residues(samples.data(), 1, &order, q.data(), res.data()));
+    q.resize(order);
+    return data::LpcEncodedData(order, bitsPerSample, std::move(q), std::move(res));
+}
+
+SampleGenerator::SampleGenerator(const data::LpcEncodedData &encodedData) : encoded(encodedData) {}
+
+// lpc::SampleGenerator::process (src/lpc/sample_generator.cpp:32-39)
+data::LpcDecodedData SampleGenerator::process()
+{
+    ensure_device();
+    if (encoded.residues.size() != kFrame)
+        raise("sela_b200: lpc::SampleGenerator needs exactly 2048 residues (the codec's frame size)");
+    uint8_t order = encoded.optimalLpcOrder;
+    std::vector<int32_t> q(SELAB200_MAX_LPC_ORDER, 0), out(kFrame);
+    std::copy_n(encoded.quantizedReflectionCoefficients.begin(),
+                std::min<size_t>(encoded.quantizedReflectionCoefficients.size(), q.size()), q.begin());
+    check(selab200_lpc_samples(encoded.residues.data(), 1, &order, q.data(), out.data()));
+    return data::LpcDecodedData(encoded.bitsPerSample, std::move(out));
+}
+
+} // namespace lpc
+
+// ------------------------------------------------------------------ frame --
+
+namespace frame {
+
+FrameEncoder::FrameEncoder(const data::WavFrame &wavFrame) : wavFrame(wavFrame) {}
+
+// frame::FrameEncoder::process (src/frame/frame_encoder.cpp:11-102)
+data::SelaFrame FrameEncoder::process()
+{
+    ensure_device();
+    const uint32_t channels = (uint32_t)wavFrame.samples.size();
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        raise("sela_b200: unsupported channel count");
+    for (const std::vector<int32_t> &plane : wavFrame.samples)
+        if (plane.size() != kFrame)
+            raise("sela_b200: frame::FrameEncoder needs 2048 samples per channel (the codec's frame size)");
+    std::vector<int16_t> pcm((size_t)kFrame * channels);
+    for (uint32_t j = 0; j < kFrame; j++)
+        for (uint32_t c = 0; c < channels; c++)
+            pcm[(size_t)j * channels + c] = narrow_sample(wavFrame.samples[c][j]);
+    std::vector<selab200_subframe_desc> descs(channels);
+    const size_t cap = selab200_encode_words_bound(1, channels);
+    std::vector<uint32_t> words(cap);
+    size_t used = 0;
+    check(selab200_encode_frames(pcm.data(), 1, channels, descs.data(), words.data(), cap, &used));
+    return frame_from_descs(descs.data(), channels, words.data(), wavFrame.bitsPerSample);
+}
+
+FrameDecoder::FrameDecoder(const data::SelaFrame &selaFrame) : selaFrame(selaFrame) {}
+
+// frame::FrameDecoder::process (src/frame/frame_decoder.cpp:11-72)
+data::WavFrame FrameDecoder::process()
+{
+    ensure_device();
+    const uint32_t channels = (uint32_t)selaFrame.subFrames.size();
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        raise("sela_b200: unsupported channel count");
+    std::vector<selab200_subframe_desc> descs(channels);
+    std::vector<uint32_t> words(frame_words(selaFrame) + 4);
+    size_t cursor = 0;
+    flatten_frame(selaFrame, descs.data(), words.data(), cursor);
+    std::vector<int16_t> pcm((size_t)kFrame * channels);
+    check(selab200_decode_frames(descs.data(), 1, channels, words.data(), cursor, pcm.data()));
+    std::vector<std::vector<int32_t>> planes(channels, std::vector<int32_t>(kFrame));
+    for (uint32_t j = 0; j < kFrame; j++)
+        for (uint32_t c = 0; c < channels; c++)
+            planes[c][j] = pcm[(size_t)j * channels + c];
+    return data::WavFrame(selaFrame.bitsPerSample, std::move(planes));
+}
+
+} // namespace frame
+
+// ------------------------------------------------------------------- file --
+
+namespace file {
+
+// file::WavFile::WavFile (src/file/wav_file.cpp:7-37): canonical 44-byte header fields
+WavFile::WavFile(uint32_t sampleRate, uint16_t bitsPerSample, uint16_t numChannels, std::vector<data::WavFrame> &&wavFrames)
+{
+    size_t payload = 0;
+    for (const data::WavFrame &f : wavFrames)
+        payload += f.samples.size() * (f.samples.empty() ? 0 : f.samples[0].size()) * (bitsPerSample / 8);
+    wavChunk.chunkId = "RIFF";
+    wavChunk.chunkSize = (uint32_t)(payload + 36);
+    wavChunk.format = "WAVE";
+    data::WavFormatSubChunk &fmt = wavChunk.formatSubChunk;
+    fmt.subChunkId = "fmt ";
+    fmt.subChunkSize = 16;
+    fmt.audioFormat = 1;
+    fmt.numChannels = numChannels;
+    fmt.sampleRate = sampleRate;
+    fmt.byteRate = (sampleRate * numChannels * bitsPerSample) / 8;
+    fmt.blockAlign = (uint16_t)((numChannels * bitsPerSample) / 8);
+    fmt.bitsPerSample = bitsPerSample;
+    data::WavDataSubChunk &dat = wavChunk.dataSubChunk;
+    dat.subChunkId = "data";
+    dat.subChunkSize = (uint32_t)payload;
+    dat.bitsPerSample = (uint8_t)bitsPerSample;
+    dat.channels = (uint8_t)numChannels;
+    dat.wavFrames = std::move(wavFrames);
+}
+
+// file::WavFile::readFromFile (src/file/wav_file.cpp:39-179): same acceptance rules and messages
+void WavFile::readFromFile(std::ifstream &inputFile)
+{
+    const std::vector<char> contents = slurp(inputFile);
+    const Bytes rd{contents};
+    if (contents.size() < 44)
+        raise("File is too small, probably not a wav file.");
+    wavChunk.chunkId = rd.tag(0);
+    if (wavChunk.chunkId != "RIFF")
+        raise("chunkId is not RIFF, probably not a wav file.");
+    wavChunk.chunkSize = rd.u32(4);
+    if ((size_t)wavChunk.chunkSize > contents.size())
+        raise("chunkSize exceeds file size, probably a corrupted file");
+    wavChunk.format = rd.tag(8);
+    if (wavChunk.format != "WAVE")
+        raise("format is not WAVE, probably not a wav file.");
+
+    bool haveFmt = false, haveData = false;
+    size_t at = 12;
+    while (at < contents.size()) {
+        if (at + 8 > contents.size())
+            raise("truncated sub-chunk header, probably a corrupted file");
+        const std::string id = rd.tag(at);
+        const uint32_t size = rd.u32(at + 4);
+        const size_t body = at + 8;
+        if (body + size > contents.size())
+            raise("sub-chunk exceeds file size, probably a corrupted file");
+        if (id == "fmt ") {
+            if (size < 16)
+                raise("fmt subChunk is too small");
+            data::WavFormatSubChunk fmt;
+            fmt.subChunkId = id;
+            fmt.subChunkSize = size;
+            fmt.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
+            fmt.audioFormat = (int16_t)rd.u16(body);
+            fmt.numChannels = (uint16_t)rd.u16(body + 2);
+            fmt.sampleRate = rd.u32(body + 4);
+            fmt.byteRate = rd.u32(body + 8);
+            fmt.blockAlign = (uint16_t)rd.u16(body + 12);
+            fmt.bitsPerSample = (uint16_t)rd.u16(body + 14);
+            if (fmt.bitsPerSample != 16)
+                raise("Only 16bits per sample wav is supported.");
+            wavChunk.formatSubChunk = fmt;
+            haveFmt = true;
+        } else if (id == "data") {
+            if (!haveFmt)
+                raise("Probably corrupt wav, data subChunk present without fmt subChunk.");
+            data::WavDataSubChunk dat;
+            dat.subChunkId = id;
+            dat.subChunkSize = size;
+            dat.bitsPerSample = 0; // the reference leaves these two zero as well (wav_file.cpp:84-85,134-135)
+            dat.channels = 0;
+            dat.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
+            wavChunk.dataSubChunk = dat;
+            haveData = true;
+        } else {
+            data::WavSubChunk other;
+            other.subChunkId = id;
+            other.subChunkSize = size;
+            other.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
+            wavChunk.wavSubChunks.push_back(other);
+        }
+        at = body + size;
+    }
+    if (!haveFmt)
+        raise("fmt subChunk is missing from file");
+    if (!haveData)
+        raise("data subChunk is missing from file");
+    demuxSamples();
+}
+
+// file::WavFile::demuxSamples (src/file/wav_file.cpp:181-220): whole frames only, the tail is dropped
+void WavFile::demuxSamples()
+{
+    const uint32_t channels = wavChunk.formatSubChunk.numChannels;
+    if (channels == 0)
+        raise("fmt subChunk declares zero channels");
+    const std::vector<int8_t> &raw = wavChunk.dataSubChunk.subChunkData;
+    const size_t sampleCount = (raw.size() * 8) / wavChunk.formatSubChunk.bitsPerSample;
+    const size_t n_frames = sampleCount / (samplesPerChannelPerFrame * channels);
+    std::vector<data::WavFrame> &frames = wavChunk.dataSubChunk.wavFrames;
+    frames.clear();
+    frames.reserve(n_frames);
+    const int16_t *pcm = reinterpret_cast<const int16_t *>(raw.data()); // little-endian host
+    for (size_t f = 0; f < n_frames; f++) {
+        std::vector<std::vector<int32_t>> planes(channels, std::vector<int32_t>(samplesPerChannelPerFrame));
+        const int16_t *src = pcm + f * samplesPerChannelPerFrame * channels;
+        for (size_t j = 0; j < samplesPerChannelPerFrame; j++)
+            for (uint32_t c = 0; c < channels; c++)
+                planes[c][j] = src[j * channels + c];
+        frames.push_back(data::WavFrame((uint8_t)wavChunk.formatSubChunk.bitsPerSample, std::move(planes)));
+    }
+}
+
+// file::WavFile::writeToFile (src/file/wav_file.cpp:222-267): same bytes for every channel count
+// (the reference has a fast path for stereo only; the layout is identical)
+void WavFile::writeToFile(std::ofstream &outputFile)
+{
+    const data::WavFormatSubChunk &fmt = wavChunk.formatSubChunk;
+    outputFile << wavChunk.chunkId;
+    put(outputFile, wavChunk.chunkSize);
+    outputFile << wavChunk.format;
+    outputFile << fmt.subChunkId;
+    put(outputFile, fmt.subChunkSize);
+    put(outputFile, fmt.audioFormat);
+    put(outputFile, fmt.numChannels);
+    put(outputFile, fmt.sampleRate);
+    put(outputFile, fmt.byteRate);
+    put(outputFile, fmt.blockAlign);
+    put(outputFile, fmt.bitsPerSample);
+    outputFile << wavChunk.dataSubChunk.subChunkId;
+    put(outputFile, wavChunk.dataSubChunk.subChunkSize);
+    std::vector<int16_t> block;
+    for (const data::WavFrame &f : wavChunk.dataSubChunk.wavFrames) {
+        const size_t channels = f.samples.size();
+        const size_t n = channels ? f.samples[0].size() : 0;
+        block.resize(n * channels);
+        for (size_t j = 0; j < n; j++)
+            for (size_t c = 0; c < channels; c++)
+                block[j * channels + c] = (int16_t)(uint16_t)f.samples[c][j];
+        outputFile.write(reinterpret_cast<const char *>(block.data()), (std::streamsize)(block.size() * 2));
+    }
+}
+
+// file::SelaFile::SelaFile (src/file/sela_file.cpp:10-17)
+SelaFile::SelaFile(uint32_t sampleRate, uint16_t bitsPerSample, uint8_t channels, std::vector<data::SelaFrame> &&frames)
+    : selaFrames(frames)
+{
+    selaHeader.sampleRate = sampleRate;
+    selaHeader.bitsPerSample = bitsPerSample;
+    selaHeader.channels = channels;
+    selaHeader.numFrames = (uint32_t)selaFrames.size();
+}
+
+// file::SelaFile::readFromFile (src/file/sela_file.cpp:19-103).  Container: 15-byte header
+// ("SeLa", rate u32, bits u16, channels u8, frames u32) then per frame the sync word
+// 0xAA55FF00 and per subframe 3+4 header bytes, refl words, 5 header bytes, residue words.
+// Stops quietly at the first bad sync word, as the reference does; unlike it, never reads
+// past the end of the buffer.
+void SelaFile::readFromFile(std::ifstream &inputFile)
+{
+    const std::vector<char> contents = slurp(inputFile);
+    const Bytes rd{contents};
+    if (contents.size() < 15)
+        raise("File is too small, probably not a sela file.");
+    if (rd.tag(0) != "SeLa")
+        raise("Magic number is incorrect, probably not a sela file.");
+    selaHeader.sampleRate = rd.u32(4);
+    selaHeader.bitsPerSample = (uint16_t)rd.u16(8);
+    selaHeader.channels = (uint8_t)rd.u8(10);
+    selaHeader.numFrames = rd.u32(11);
+    size_t at = 15;
+    auto need = [&](size_t n) {
+        if (at + n > contents.size())
+            raise("sela file is truncated");
+    };
+    auto words_at = [&](size_t count) {
+        need(count * 4);
+        std::vector<uint32_t> w(count);
+        if (count)
+            std::memcpy(w.data(), contents.data() + at, count * 4); // little-endian host
+        at += count * 4;
+        return w;
+    };
+    selaFrames.clear();
+    selaFrames.reserve(selaHeader.numFrames);
+    for (uint32_t f = 0; f < selaHeader.numFrames; f++) {
+        if (at + 4 > contents.size() || rd.u32(at) != 0xAA55FF00u)
+            break;
+        at += 4;
+        data::SelaFrame frame((uint8_t)selaHeader.bitsPerSample);
+        frame.subFrames.reserve(selaHeader.channels);
+        for (uint32_t c = 0; c < selaHeader.channels; c++) {
+            need(7);
+            const uint8_t channel = (uint8_t)rd.u8(at), type = (uint8_t)rd.u8(at + 1), parent = (uint8_t)rd.u8(at + 2);
+            const uint8_t reflK = (uint8_t)rd.u8(at + 3);
+            const uint16_t reflInts = (uint16_t)rd.u16(at + 4);
+            const uint8_t order = (uint8_t)rd.u8(at + 6);
+            at += 7;
+            data::RiceEncodedData refl(reflK, order, words_at(reflInts));
+            need(5);
+            const uint8_t resK = (uint8_t)rd.u8(at);
+            const uint16_t resInts = (uint16_t)rd.u16(at + 1), samples = (uint16_t)rd.u16(at + 3);
+            at += 5;
+            data::RiceEncodedData res(resK, samples, words_at(resInts));
+            frame.subFrames.push_back(data::SelaSubFrame(channel, type, parent, refl, res));
+        }
+        selaFrames.push_back(frame);
+    }
+}
+
+// file::SelaFile::writeToFile (src/file/sela_file.cpp:105-137)
+void SelaFile::writeToFile(std::ofstream &outputFile)
+{
+    outputFile.write(reinterpret_cast<const char *>(selaHeader.magicNumber), 4);
+    put(outputFile, selaHeader.sampleRate);
+    put(outputFile, selaHeader.bitsPerSample);
+    put(outputFile, selaHeader.channels);
+    put(outputFile, selaHeader.numFrames);
+    for (const data::SelaFrame &frame : selaFrames) {
+        put(outputFile, frame.syncWord);
+        for (const data::SelaSubFrame &s : frame.subFrames) {
+            put(outputFile, s.channel);
+            put(outputFile, s.subFrameType);
+            put(outputFile, s.parentChannelNumber);
+            put(outputFile, s.reflectionCoefficientRiceParam);
+            put(outputFile, s.reflectionCoefficientRequiredInts);
+            put(outputFile, s.optimumLpcOrder);
+            outputFile.write(reinterpret_cast<const char *>(s.encodedReflectionCoefficients.data()),
+                             (std::streamsize)(s.encodedReflectionCoefficients.size() * 4));
+            put(outputFile, s.residueRiceParam);
+            put(outputFile, s.residueRequiredInts);
+            put(outputFile, s.samplesPerChannel);
+            outputFile.write(reinterpret_cast<const char *>(s.encodedResidues.data()),
+                             (std::streamsize)(s.encodedResidues.size() * 4));
+        }
+    }
+}
+
+} // namespace file
+
+// ------------------------------------------------------------------- sela --
+
+namespace sela {
+
+void Encoder::readFrames() { wavFile.readFromFile(ifStream); }
+
+// sela::Encoder::processFrames (src/sela/encoder.cpp:40-92): the reference fans the frames
+// out over hardware_concurrency() threads; here the whole file is ONE batch on the GPU
+// and the frames come back in order.
+void Encoder::processFrames(std::vector<data::SelaFrame> &encodedSelaFrames)
+{
+    ensure_device();
+    const std::vector<data::WavFrame> &frames = wavFile.wavChunk.dataSubChunk.wavFrames;
+    const uint32_t n_frames = (uint32_t)frames.size();
+    encodedSelaFrames.reserve(n_frames);
+    if (n_frames == 0)
+        return;
+    const uint32_t channels = (uint32_t)frames[0].samples.size();
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        raise("sela_b200: unsupported channel count");
+    const size_t n_samples = (size_t)n_frames * channels * kFrame;
+    Pinned<int16_t> pcm(n_samples);
+    const std::vector<int8_t> &raw = wavFile.wavChunk.dataSubChunk.subChunkData;
+    if (raw.size() >= n_samples * 2) {
+        std::memcpy(pcm.p, raw.data(), n_samples * 2); // the data chunk IS the interleaved layout
+    } else {
+        for (uint32_t f = 0; f < n_frames; f++)
+            for (uint32_t j = 0; j < kFrame; j++)
+                for (uint32_t c = 0; c < channels; c++)
+                    pcm.p[((size_t)f * kFrame + j) * channels + c] = narrow_sample(frames[f].samples[c][j]);
+    }
+    const size_t cap = selab200_encode_words_bound(n_frames, channels);
+    Pinned<selab200_subframe_desc> descs((size_t)n_frames * channels);
+    Pinned<uint32_t> words(cap);
+    size_t used = 0;
+    check(selab200_encode_frames(pcm.p, n_frames, channels, descs.p, words.p, cap, &used));
+    const uint8_t bits = frames[0].bitsPerSample;
+    for (uint32_t f = 0; f < n_frames; f++)
+        encodedSelaFrames.push_back(frame_from_descs(descs.p + (size_t)f * channels, channels, words.p, bits));
+}
+
+// sela::Encoder::process (src/sela/encoder.cpp:94-99)
+file::SelaFile Encoder::process()
+{
+    std::vector<data::SelaFrame> frames;
+    readFrames();
+    processFrames(frames);
+    const data::WavFormatSubChunk &fmt = wavFile.wavChunk.formatSubChunk;
+    return file::SelaFile(fmt.sampleRate, fmt.bitsPerSample, (uint8_t)fmt.numChannels, std::move(frames));
+}
+
+void Decoder::readFrames() { selaFile.readFromFile(ifStream); }
+
+// sela::Decoder::processFrames (src/sela/decoder.cpp:41-92)
+void Decoder::processFrames(std::vector<data::WavFrame> &decodedWavFrames)
+{
+    ensure_device();
+    const std::vector<data::SelaFrame> &frames = selaFile.selaFrames;
+    const uint32_t n_frames = (uint32_t)frames.size();
+    decodedWavFrames.reserve(n_frames);
+    if (n_frames == 0)
+        return;
+    const uint32_t channels = (uint32_t)frames[0].subFrames.size();
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        raise("sela_b200: unsupported channel count");
+    size_t total_words = 0;
+    for (const data::SelaFrame &f : frames) {
+        if (f.subFrames.size() != channels)
+            raise("sela_b200: frames with differing channel counts");
+        total_words += frame_words(f);
+    }
+    Pinned<selab200_subframe_desc> descs((size_t)n_frames * channels);
+    Pinned<uint32_t> words(total_words + 4);
+    size_t cursor = 0;
+    for (uint32_t f = 0; f < n_frames; f++)
+        flatten_frame(frames[f], descs.p + (size_t)f * channels, words.p, cursor);
+    Pinned<int16_t> pcm((size_t)n_frames * channels * kFrame);
+    check(selab200_decode_frames(descs.p, n_frames, channels, words.p, cursor, pcm.p));
+    const uint8_t bits = (uint8_t)selaFile.selaHeader.bitsPerSample;
+    for (uint32_t f = 0; f < n_frames; f++) {
+        std::vector<std::vector<int32_t>> planes(channels, std::vector<int32_t>(kFrame));
+        const int16_t *src = pcm.p + (size_t)f * channels * kFrame;
+        for (uint32_t j = 0; j < kFrame; j++)
+            for (uint32_t c = 0; c < channels; c++)
+                planes[c][j] = src[(size_t)j * channels + c];
+        decodedWavFrames.push_back(data::WavFrame(bits, std::move(planes)));
+    }
+}
+
+// sela::Decoder::process (src/sela/decoder.cpp:94-99)
+file::WavFile Decoder::process()
+{
+    std::vector<data::WavFrame> frames;
+    readFrames();
+    processFrames(frames);
+    return file::WavFile(selaFile.selaHeader.sampleRate, selaFile.selaHeader.bitsPerSample,
+                         selaFile.selaHeader.channels, std::move(frames));
+}
+
+void Player::play(const file::WavFile &)
+{
+    raise("playback is not part of this build (libao output is out of scope); decode with -d instead");
+}
+
+} // namespace sela

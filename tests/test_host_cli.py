@@ -1,0 +1,122 @@
+"""The C++ mirror of the reference interface and the CLI built on it (sela_b200/host).
+
+CPU part: the container code (WAV / .sela readers and writers) against the compiled reference.
+GPU part: `sela -e/-d` byte-for-byte against the reference CLI (oracle/_ref/sela_ref_cli, which
+travels to the GPU box as a prebuilt binary), the reference's own main.cpp linked against this
+library, and the reference's unit tests re-expressed on the mirror classes."""
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+from sela_b200 import synth, wavio
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+BIN = ROOT / "sela_b200" / "host" / "bin"
+REF_CLI = ROOT / "oracle" / "_ref" / "sela_ref_cli"
+
+
+def _run(*cmd, ok=True):
+    p = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=600)
+    if ok:
+        assert p.returncode == 0, (cmd, p.stdout[-400:], p.stderr[-400:])
+    return p
+
+
+def _ensure_built():
+    if not (BIN / "sela").exists():
+        subprocess.run(["make", "-C", str(ROOT / "sela_b200" / "host")], check=True, capture_output=True)
+
+
+def _cases(tmp):
+    out = {}
+    pcm = synth.sine_noise(44100, 2, n_frames=20, seed=1)
+    pcm[2048 * 4:2048 * 9, 1] = pcm[2048 * 4:2048 * 9, 0] - (pcm[2048 * 4:2048 * 9, 1] >> 5)
+    pcm = np.concatenate([pcm, pcm[:777]])                       # tail that is not a whole frame: dropped
+    wavio.write_wav(tmp / "stereo.wav", pcm, 44100, extra_chunks=[(b"LIST", b"INFOabcd1234")])
+    out["stereo"] = tmp / "stereo.wav"
+    wavio.write_wav(tmp / "mono.wav", synth.sine_noise(22050, 1, n_frames=7, seed=5), 22050)
+    out["mono"] = tmp / "mono.wav"
+    wavio.write_wav(tmp / "oct.wav", synth.sine_noise(48000, 8, n_frames=5, seed=2), 48000)
+    out["oct"] = tmp / "oct.wav"
+    return out
+
+
+# ------------------------------------------------------------------ CPU --
+
+@pytest.mark.ref
+def test_container_code_matches_reference(tmp_path):
+    """file::SelaFile read->write is byte-identical on reference-produced files; file::WavFile
+    read->(canonical)write equals what the reference decoder writes back (header + tail drop)."""
+    _ensure_built()
+    for name, wav in _cases(tmp_path).items():
+        ref_sela, ref_wav = tmp_path / (name + ".ref.sela"), tmp_path / (name + ".ref.wav")
+        _run(REF_CLI, "-e", wav, ref_sela)
+        _run(REF_CLI, "-d", ref_sela, ref_wav)
+        _run(BIN / "container_check", "sela", ref_sela, tmp_path / "rt.sela")
+        assert (tmp_path / "rt.sela").read_bytes() == ref_sela.read_bytes(), name
+        _run(BIN / "container_check", "wav", wav, tmp_path / "rt.wav")
+        assert (tmp_path / "rt.wav").read_bytes() == ref_wav.read_bytes(), name
+
+
+def test_container_errors_match_reference_messages(tmp_path):
+    _ensure_built()
+    (tmp_path / "tiny.wav").write_bytes(b"RIFF")
+    p = _run(BIN / "container_check", "wav", tmp_path / "tiny.wav", tmp_path / "o", ok=False)
+    assert p.returncode == 1 and "File is too small, probably not a wav file." in p.stderr
+    (tmp_path / "bad.sela").write_bytes(b"NotSela" + bytes(20))
+    p = _run(BIN / "container_check", "sela", tmp_path / "bad.sela", tmp_path / "o", ok=False)
+    assert p.returncode == 1 and "Magic number is incorrect" in p.stderr
+    pcm8 = np.zeros((4096, 1), np.int16)
+    wavio.write_wav(tmp_path / "w.wav", pcm8, 8000)
+    raw = bytearray((tmp_path / "w.wav").read_bytes())
+    raw[34] = 24                                                   # bitsPerSample = 24
+    (tmp_path / "w24.wav").write_bytes(bytes(raw))
+    p = _run(BIN / "container_check", "wav", tmp_path / "w24.wav", tmp_path / "o", ok=False)
+    assert p.returncode == 1 and "Only 16bits per sample wav is supported." in p.stderr
+
+
+# ------------------------------------------------------------------ GPU --
+
+@pytest.mark.gpu
+def test_reference_unit_tests_on_mirror_classes():
+    _ensure_built()
+    p = _run(BIN / "sela_reftests")
+    assert "All tests passed" in p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary", ["sela", "sela_refmain"])
+def test_cli_byte_parity_with_reference_cli(tmp_path, binary):
+    _ensure_built()
+    if not (BIN / binary).exists():
+        pytest.skip("%s not built (needs the reference tree at build time)" % binary)
+    have_ref = REF_CLI.exists()
+    for name, wav in _cases(tmp_path).items():
+        ours_sela, ours_wav = tmp_path / (name + ".sela"), tmp_path / (name + ".out.wav")
+        p = _run(BIN / binary, "-e", wav, ours_sela)
+        assert "Encoding: " in p.stdout
+        _run(BIN / binary, "-d", ours_sela, ours_wav)
+        if have_ref:
+            ref_sela, ref_wav = tmp_path / (name + ".ref.sela"), tmp_path / (name + ".ref.wav")
+            _run(REF_CLI, "-e", wav, ref_sela)
+            assert ours_sela.read_bytes() == ref_sela.read_bytes(), name          # bit-identical .sela
+            _run(REF_CLI, "-d", ours_sela, ref_wav)                               # reference decodes ours
+            assert ours_wav.read_bytes() == ref_wav.read_bytes(), name            # bit-identical .wav
+        # lossless against the source (whole frames only)
+        _, ch, pcm_out = wavio.read_wav_pcm(ours_wav)
+        data_at = wav.read_bytes().index(b"data") + 8
+        pcm_src = np.frombuffer(wav.read_bytes()[data_at:], dtype="<i2")
+        pcm_src = pcm_src[: (pcm_src.size // (2048 * ch)) * 2048 * ch].reshape(-1, ch)
+        assert np.array_equal(pcm_out, pcm_src), name
+
+
+@pytest.mark.gpu
+def test_cli_error_convention(tmp_path):
+    _ensure_built()
+    (tmp_path / "junk.wav").write_bytes(b"not a wav file at all, but long enough to pass the size check....")
+    p = _run(BIN / "sela", "-e", tmp_path / "junk.wav", tmp_path / "o.sela", ok=False)
+    assert p.returncode == 1 and "chunkId is not RIFF" in p.stderr
+    p = _run(BIN / "sela", ok=True)
+    assert "Usage:" in p.stdout

@@ -170,57 +170,78 @@ __device__ __forceinline__ Emit choose_unit(const UnitRecord *units, uint32_t ch
 
 __global__ void __launch_bounds__(1024) k_encode_scan(EncodeParams p)
 {
-    __shared__ unsigned long long partial[1024];
+    // One CTA walks the emitted subframes in file order, 1024 at a time: coalesced unit-record
+    // loads, a shuffle-based block scan of the sizes, descriptors out; the running fill level is
+    // carried from tile to tile (and, through *words_used, from chunk to chunk of a pipelined call).
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
     const uint32_t n_sub = p.n_frames * p.channels;
-    const uint32_t per = (n_sub + 1023) / 1024;
-    const uint32_t lo = min(threadIdx.x * per, n_sub), hi = min(lo + per, n_sub);
-    unsigned long long sum = 0;
+    const int lane = lane_id(), warp = warp_id();
+    if (threadIdx.x == 0)
+        carry = *p.words_used;
     bool bad = false;
-    for (uint32_t sub = lo; sub < hi; sub++) {
-        const Emit e = choose_unit(p.units, p.channels, sub);
-        const UnitRecord u = p.units[e.unit];
-        sum += (unsigned long long)u.refl_words + u.res_words;
-        bad |= u.flags != 0 || u.refl_words > 0xffffu || u.res_words > 0xffffu;
-    }
-    partial[threadIdx.x] = sum;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned long long v = threadIdx.x >= o ? partial[threadIdx.x - o] : 0;
+    for (uint32_t tile = 0; tile < n_sub; tile += 1024) {
+        const uint32_t sub = tile + threadIdx.x;
+        Emit e;
+        UnitRecord u;
+        unsigned long long size = 0;
+        if (sub < n_sub) {
+            e = choose_unit(p.units, p.channels, sub);
+            u = p.units[e.unit];
+            size = (unsigned long long)u.refl_words + u.res_words;
+            bad |= u.flags != 0 || u.refl_words > 0xffffu || u.res_words > 0xffffu;
+        }
+        unsigned long long incl = size;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            warp_tot[warp] = incl;
         __syncthreads();
-        partial[threadIdx.x] += v;
+        if (warp == 0) {
+            unsigned long long w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(kFull, w, o);
+                if (lane >= o)
+                    w += t;
+            }
+            warp_tot[lane] = w; // inclusive over warps
+        }
         __syncthreads();
-    }
-    // *words_used is in/out: the arena fill level before this batch (0, or where the
-    // previous chunk of a pipelined call stopped) and after it
-    const unsigned long long base = *p.words_used;
-    __syncthreads();
-    unsigned long long off = base + partial[threadIdx.x] - sum;
-    if (threadIdx.x == 1023) {
-        *p.words_used = base + partial[1023];
-        if (base + partial[1023] > p.capacity)
-            raise_status(p.status, SELAB200_ERR_CAPACITY);
+        const unsigned long long base = carry + (warp ? warp_tot[warp - 1] : 0);
+        if (sub < n_sub) {
+            const unsigned long long off = base + incl - size;
+            selab200_subframe_desc v;
+            v.channel = (uint8_t)(sub % p.channels);
+            v.subframe_type = (uint8_t)e.type;
+            v.parent_channel = (uint8_t)e.parent;
+            v.refl_rice_param = (uint8_t)u.refl_k;
+            v.refl_words = (uint16_t)u.refl_words;
+            v.lpc_order = (uint8_t)u.order;
+            v.res_rice_param = (uint8_t)u.res_k;
+            v.res_words = (uint16_t)u.res_words;
+            v.samples = (uint16_t)kFrame;
+            v.reserved = 0;
+            v.refl_offset = off;
+            v.res_offset = off + u.refl_words;
+            p.descs[sub] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += warp_tot[31];
+        __syncthreads();
     }
     if (bad)
         raise_status(p.status, SELAB200_ERR_RANGE); // a stream the uint16 word counts cannot describe
-    for (uint32_t sub = lo; sub < hi; sub++) {
-        const Emit e = choose_unit(p.units, p.channels, sub);
-        const UnitRecord u = p.units[e.unit];
-        selab200_subframe_desc v;
-        v.channel = (uint8_t)(sub % p.channels);
-        v.subframe_type = (uint8_t)e.type;
-        v.parent_channel = (uint8_t)e.parent;
-        v.refl_rice_param = (uint8_t)u.refl_k;
-        v.refl_words = (uint16_t)u.refl_words;
-        v.lpc_order = (uint8_t)u.order;
-        v.res_rice_param = (uint8_t)u.res_k;
-        v.res_words = (uint16_t)u.res_words;
-        v.samples = (uint16_t)kFrame;
-        v.reserved = 0;
-        v.refl_offset = off;
-        v.res_offset = off + u.refl_words;
-        p.descs[sub] = v;
-        off += (unsigned long long)u.refl_words + u.res_words;
+    if (threadIdx.x == 0) {
+        *p.words_used = carry;
+        if (carry > p.capacity)
+            raise_status(p.status, SELAB200_ERR_CAPACITY);
     }
 }
 

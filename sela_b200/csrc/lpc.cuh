@@ -109,7 +109,17 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
     }
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     double p1 = 0.0, p2 = 0.0, p3 = 0.0; // d[4G-1], d[4G-2], d[4G-3]
-    const double2 *ring2 = reinterpret_cast<const double2 *>(sm.ring);
+    const char *ringb = reinterpret_cast<const char *>(sm.ring);
+    // Groups are processed 8 at a time (g = g0 + i, g0 a multiple of 8), which makes the
+    // swizzle bit of every access loop-invariant: for the broadcast group it is (i>>2)&1, a
+    // compile-time constant; for the lane's own group G = g - lane it is ((i - lane)>>2)&1.
+    // The physical byte offset of chunk 2G is then (32*g0 + own_off[i]) & 4095.
+    int own_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int rel = i - lane;
+        own_off[i] = 16 * (2 * rel + ((rel >> 2) & 1));
+    }
 
     for (int tile = 0; tile < kFrame / 256; tile++) {
         __syncwarp();
@@ -119,37 +129,42 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
             sm.ring[ring_index(j)] = dsub(sample_to_x(sig.at(j)), mean);
         }
         __syncwarp();
-#pragma unroll 2
-        for (int g = tile * 64; g < tile * 64 + 64; g++) {
-            const int G = g - lane;
-            const double2 o0 = ring2[ring_chunk(2 * G)];
-            const double2 o1 = ring2[ring_chunk(2 * G + 1)];
-            const double2 b0 = ring2[ring_chunk(2 * g)];
-            const double2 b1 = ring2[ring_chunk(2 * g + 1)];
-            const double c0 = o0.x, c1 = o0.y, c2 = o1.x, c3 = o1.y; // d[4G..4G+3]
-            // u = 0  (j = 4g)
-            acc0 = dadd(acc0, dmul(b0.x, c0));
-            acc1 = dadd(acc1, dmul(b0.x, p1));
-            acc2 = dadd(acc2, dmul(b0.x, p2));
-            acc3 = dadd(acc3, dmul(b0.x, p3));
-            // u = 1
-            acc0 = dadd(acc0, dmul(b0.y, c1));
-            acc1 = dadd(acc1, dmul(b0.y, c0));
-            acc2 = dadd(acc2, dmul(b0.y, p1));
-            acc3 = dadd(acc3, dmul(b0.y, p2));
-            // u = 2
-            acc0 = dadd(acc0, dmul(b1.x, c2));
-            acc1 = dadd(acc1, dmul(b1.x, c1));
-            acc2 = dadd(acc2, dmul(b1.x, c0));
-            acc3 = dadd(acc3, dmul(b1.x, p1));
-            // u = 3
-            acc0 = dadd(acc0, dmul(b1.y, c3));
-            acc1 = dadd(acc1, dmul(b1.y, c2));
-            acc2 = dadd(acc2, dmul(b1.y, c1));
-            acc3 = dadd(acc3, dmul(b1.y, c0));
-            p1 = c3;
-            p2 = c2;
-            p3 = c1;
+        for (int blk = 0; blk < 8; blk++) {
+            const int gb = (tile * 64 + blk * 8) * 32; // byte offset of chunk 2*g0 before wrapping
+            const char *bbase = ringb + (gb & 4095);    // 256-byte aligned: the 8 broadcast groups never wrap
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int oo = (gb + own_off[i]) & 4095;
+                const double2 o0 = *reinterpret_cast<const double2 *>(ringb + oo);
+                const double2 o1 = *reinterpret_cast<const double2 *>(ringb + (oo ^ 16));
+                constexpr int kSw[8] = {0, 0, 0, 0, 16, 16, 16, 16};
+                const double2 b0 = *reinterpret_cast<const double2 *>(bbase + ((32 * i) ^ kSw[i]));
+                const double2 b1 = *reinterpret_cast<const double2 *>(bbase + ((32 * i + 16) ^ kSw[i]));
+                const double c0 = o0.x, c1 = o0.y, c2 = o1.x, c3 = o1.y; // d[4G..4G+3]
+                // u = 0  (j = 4g)
+                acc0 = dadd(acc0, dmul(b0.x, c0));
+                acc1 = dadd(acc1, dmul(b0.x, p1));
+                acc2 = dadd(acc2, dmul(b0.x, p2));
+                acc3 = dadd(acc3, dmul(b0.x, p3));
+                // u = 1
+                acc0 = dadd(acc0, dmul(b0.y, c1));
+                acc1 = dadd(acc1, dmul(b0.y, c0));
+                acc2 = dadd(acc2, dmul(b0.y, p1));
+                acc3 = dadd(acc3, dmul(b0.y, p2));
+                // u = 2
+                acc0 = dadd(acc0, dmul(b1.x, c2));
+                acc1 = dadd(acc1, dmul(b1.x, c1));
+                acc2 = dadd(acc2, dmul(b1.x, c0));
+                acc3 = dadd(acc3, dmul(b1.x, p1));
+                // u = 3
+                acc0 = dadd(acc0, dmul(b1.y, c3));
+                acc1 = dadd(acc1, dmul(b1.y, c2));
+                acc2 = dadd(acc2, dmul(b1.y, c1));
+                acc3 = dadd(acc3, dmul(b1.y, c0));
+                p1 = c3;
+                p2 = c2;
+                p3 = c1;
+            }
         }
     }
     __syncwarp();

@@ -29,25 +29,27 @@ struct RiceChoice {
 // calculateOptimumRiceParam (rice_encoder.cpp:20-33): first arg-min over k = 0..19 of
 // sum(u >> k) + n*(1 + k).  Val(i) returns the i-th int32 input, i < n <= 2048.
 // Every lane returns the same result.
-template <typename Val>
-__device__ RiceChoice warp_rice_choose(const Val &val, int n)
+//
+// The 20 sums are not accumulated one by one.  With S_k = sum_i (u_i >> k) and C_k the
+// number of inputs whose bit k is set,  S_k = 2*S_{k+1} + C_k  exactly, so S_19 plus
+// the 19 bit counts suffice.  The counts come from a bit-sliced (Harley-Seal) vertical
+// counter: each lane folds its 64 words into 7 planes with carry-save adders (about two
+// LOP3 per word instead of forty shift+adds), and a ballot per (plane, bit) finishes the
+// cross-lane sum.
+__device__ __forceinline__ void csa(uint32_t &hi, uint32_t &lo, uint32_t a, uint32_t b, uint32_t c)
 {
-    const int lane = lane_id();
-    unsigned long long sums[kMaxRice];
-#pragma unroll
-    for (int k = 0; k < kMaxRice; k++)
-        sums[k] = 0;
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t u = zigzag(val(i));
-#pragma unroll
-        for (int k = 0; k < kMaxRice; k++)
-            sums[k] += u >> k;
-    }
+    const uint32_t u = a ^ b;
+    hi = (a & b) | (u & c);
+    lo = u ^ c;
+}
+
+__device__ __forceinline__ RiceChoice rice_choice_from_sums(const unsigned long long (&sums)[kMaxRice], int n)
+{
     unsigned long long best = ~0ull;
     uint32_t best_k = 0;
 #pragma unroll
     for (int k = 0; k < kMaxRice; k++) {
-        unsigned long long total = warp_sum_u64(sums[k]) + (unsigned long long)n * (1 + k);
+        const unsigned long long total = sums[k] + (unsigned long long)n * (1 + k);
         if (total < best) {
             best = total;
             best_k = k;
@@ -56,9 +58,75 @@ __device__ RiceChoice warp_rice_choose(const Val &val, int n)
     RiceChoice c;
     c.k = best_k;
     c.bits = best > 0xffffffffull ? 0xffffffffu : (uint32_t)best;
-    unsigned long long w = (best + 31) >> 5;
+    const unsigned long long w = (best + 31) >> 5;
     c.words = w > 0xffffffffull ? 0xffffffffu : (uint32_t)w;
     return c;
+}
+
+template <typename Val>
+__device__ RiceChoice warp_rice_choose(const Val &val, int n)
+{
+    const int lane = lane_id();
+    unsigned long long sums[kMaxRice];
+    if (n <= 256) {
+        // short streams (the reflection coefficients): direct accumulation
+#pragma unroll
+        for (int k = 0; k < kMaxRice; k++)
+            sums[k] = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t u = zigzag(val(i));
+#pragma unroll
+            for (int k = 0; k < kMaxRice; k++)
+                sums[k] += u >> k;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxRice; k++)
+            sums[k] = warp_sum_u64(sums[k]);
+        return rice_choice_from_sums(sums, n);
+    }
+    // bit planes of weight 1, 2, 4, ..., 64 over this lane's (up to) 64 words
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, sixteens = 0, thirtytwos = 0;
+    uint32_t s16[4];
+    unsigned long long top = 0; // sum of u >> 19
+    auto word = [&](int t) -> uint32_t {
+        const int i = lane + 32 * t;
+        const uint32_t u = i < n ? zigzag(val(i)) : 0u;
+        top += u >> (kMaxRice - 1);
+        return u & ((1u << (kMaxRice - 1)) - 1);
+    };
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        uint32_t e8[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            uint32_t f4[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int t = a * 16 + b * 8 + c * 4;
+                uint32_t ta, tb;
+                csa(ta, ones, ones, word(t), word(t + 1));
+                csa(tb, ones, ones, word(t + 2), word(t + 3));
+                csa(f4[c], twos, twos, ta, tb);
+            }
+            csa(e8[b], fours, fours, f4[0], f4[1]);
+        }
+        csa(s16[a], eights, eights, e8[0], e8[1]);
+    }
+    uint32_t x32, y32, sixtyfours;
+    csa(x32, sixteens, sixteens, s16[0], s16[1]);
+    csa(y32, sixteens, sixteens, s16[2], s16[3]);
+    csa(sixtyfours, thirtytwos, thirtytwos, x32, y32);
+    const uint32_t planes[7] = {ones, twos, fours, eights, sixteens, thirtytwos, sixtyfours};
+    sums[kMaxRice - 1] = warp_sum_u64(top);
+#pragma unroll
+    for (int k = kMaxRice - 2; k >= 0; k--) {
+        uint32_t count = 0;
+#pragma unroll
+        for (int p = 0; p < 7; p++)
+            count += (uint32_t)__popc(__ballot_sync(kFull, (planes[p] >> k) & 1u)) << p;
+        sums[k] = 2 * sums[k + 1] + count;
+    }
+    return rice_choice_from_sums(sums, n);
 }
 
 // generateEncodedBits + writeInts (rice_encoder.cpp:35-71).  Lane l codes the

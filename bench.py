@@ -172,6 +172,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi is slow to spin up
     pcm_np = make_pcm(1 + rank)
     n_frames = pcm_np.shape[0] // FRAME
     n_samples = n_frames * FRAME * CHANNELS
@@ -195,7 +196,6 @@ def run_ours(args, rank, world, local_rank):
         codec.encode(pcm)
         codec.decode(out, n_words)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()

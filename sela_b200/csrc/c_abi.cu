@@ -223,6 +223,12 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     k_rice_decode<<<blocks, 32 * kRiceWarps, 0, stream>>>(p, 1);
     if (int rc = launch_check("k_rice_decode(res)"))
         return rc;
+    p.fallback_only = 1;
+    k_synthesise_quad<<<(unsigned)((n_sub + 3) / 4), 32, 0, stream>>>(p);
+    if (int rc = launch_check("k_synthesise_quad"))
+        return rc;
+    if (channels == 2)
+        return 0; // every stereo frame is handled by the batch kernel
     const size_t smem = synthesise_smem_bytes(channels);
     if (int rc = set_smem(k_synthesise, smem))
         return rc;

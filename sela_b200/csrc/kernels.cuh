@@ -286,6 +286,7 @@ struct DecodeParams {
     int32_t *status;
     int32_t *ws_q;   // [n_sub][128]
     int32_t *ws_res; // [n_sub][2048]
+    int fallback_only;
 };
 
 // K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams, 1: residue streams.
@@ -323,7 +324,10 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p,
         raise_status(p.status, SELAB200_ERR_BITSTREAM);
 }
 
-// K6: CTA per frame; each warp synthesises TWO subframes (one per half-warp).
+__device__ __forceinline__ bool frame_needs_general(uint32_t ch, unsigned type_mask) { return ch != 2 && type_mask != 0; }
+
+// K6, general form: CTA per frame; each warp synthesises TWO subframes (one per half-warp) into
+// shared-memory planes, so any parent/child arrangement inside the frame can be resolved.
 __global__ void k_synthesise(DecodeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -361,6 +365,15 @@ __global__ void k_synthesise(DecodeParams p)
     __syncthreads();
     const bool valid = meta[2 * ch];
     int16_t *out = p.pcm_out + (size_t)frame * kFrame * ch;
+    if (p.fallback_only) {
+        // launched behind k_synthesise_quad: only frames it declines (difference coding with a
+        // channel count other than 2) are left to do
+        unsigned type_mask = 0;
+        for (uint32_t c = 0; c < ch; c++)
+            type_mask |= (unsigned)(meta[c] == 1) << c;
+        if (!valid || !frame_needs_general(ch, type_mask))
+            return;
+    }
     if (!valid) {
         for (uint32_t e = threadIdx.x; e < kFrame * ch; e += blockDim.x)
             out[e] = 0;
@@ -404,6 +417,109 @@ __global__ void k_synthesise(DecodeParams p)
         if (meta[c] == 1)
             v = planes[(size_t)meta[ch + c] * kFrame + j] - v;
         out[e] = (int16_t)(uint16_t)v;
+    }
+}
+
+// K6, batch form: one warp = four consecutive subframes of the descriptor table (stereo: two
+// frames; mono: four frames; 8 channels: half a frame).  Handles every frame except those with
+// difference-coded subframes and a channel count other than 2 (the reference's encoder never
+// produces those; k_synthesise above picks them up).
+struct QuadSmem {
+    CoefSmem cf[4];
+    double t[104];
+    int32_t stage[4][2][16];
+};
+
+__global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
+{
+    __shared__ __align__(16) QuadSmem sm;
+    const uint32_t ch = p.channels;
+    const uint32_t n_sub = p.n_frames * ch;
+    const int lane = lane_id(), q = lane >> 3, hl = lane & 7;
+    const uint32_t sub = blockIdx.x * 4 + q;
+    const bool exists = sub < n_sub;
+    const uint32_t frame = exists ? sub / ch : 0, pos = exists ? sub % ch : 0;
+
+    // ---- per-quarter validation of the whole frame (all eight lanes redundantly) ----
+    bool frame_ok = exists;
+    unsigned seen = 0, type_mask = 0;
+    selab200_subframe_desc mine;
+    memset(&mine, 0, sizeof mine);
+    if (exists) {
+        const selab200_subframe_desc *fd = p.descs + (size_t)frame * ch;
+        for (uint32_t i = 0; i < ch; i++) {
+            const selab200_subframe_desc d = fd[i];
+            const bool ok = desc_ok(d, ch, p.n_words) && !((seen >> d.channel) & 1);
+            frame_ok &= ok;
+            if (ok) {
+                seen |= 1u << d.channel;
+                type_mask |= (unsigned)(d.subframe_type & 1) << d.channel;
+            }
+            if (i == pos)
+                mine = d;
+        }
+        for (uint32_t i = 0; i < ch && frame_ok; i++) {
+            const selab200_subframe_desc d = fd[i];
+            if (d.subframe_type == 1 && ((type_mask >> d.parent_channel) & 1))
+                frame_ok = false; // a parent must be an independent subframe
+        }
+        if (!frame_ok && hl == 0)
+            raise_status(p.status, SELAB200_ERR_BITSTREAM);
+    }
+    const bool general = exists && frame_ok && frame_needs_general(ch, type_mask);
+    const bool proc = exists && frame_ok && !general;
+    const int order = proc ? mine.lpc_order : 0;
+
+    // ---- predictors of the four subframes (warp-wide routines, one subframe at a time) ----
+    for (int h = 0; h < 4; h++) {
+        const int order_h = __shfl_sync(kFull, order, 8 * h);
+        const uint32_t sub_h = blockIdx.x * 4 + h;
+        CoefSmem &cf = sm.cf[h];
+        for (int i = lane; i < 104; i += 32)
+            cf.q[i] = i < order_h ? p.ws_q[(size_t)sub_h * 128 + i] : 0;
+        __syncwarp();
+        warp_coefficients(cf, sm.t, order_h); // order 0 behaves like a zero predictor
+        warp_iir_prepare(cf, order_h);
+    }
+    int order_max = order;
+    order_max = max(order_max, __shfl_xor_sync(kFull, order_max, 8));
+    order_max = max(order_max, __shfl_xor_sync(kFull, order_max, 16));
+
+    // ---- recurrence + output ----
+    QuadIo io;
+    io.res = p.ws_res + (size_t)(exists ? sub : 0) * kFrame;
+    io.stage = &sm.stage[q][0][0];
+    const bool stereo = ch == 2;
+    const bool diff = proc && mine.subframe_type == 1;
+    const uint32_t channel = mine.channel;
+    int16_t *out = p.pcm_out + (size_t)frame * kFrame * ch;
+    auto emit = [&](int B, int kx, int ky) {
+        if (stereo) {
+            // partner quarter holds the other channel of the same frame
+            const int px = __shfl_xor_sync(kFull, kx, 8), py = __shfl_xor_sync(kFull, ky, 8);
+            const int fx = diff ? px - kx : kx, fy = diff ? py - ky : ky; // frame_decoder.cpp:64-67
+            const int gx = __shfl_xor_sync(kFull, fx, 8), gy = __shfl_xor_sync(kFull, fy, 8);
+            if (proc && channel == 0) {
+                const uint32_t w0 = ((uint32_t)fx & 0xffffu) | ((uint32_t)gx << 16);
+                const uint32_t w1 = ((uint32_t)fy & 0xffffu) | ((uint32_t)gy << 16);
+                reinterpret_cast<uint2 *>(out)[(16 * B + 2 * hl) / 2] = make_uint2(w0, w1);
+            }
+        } else if (proc) {
+            const size_t t = 16 * B + 2 * hl;
+            out[t * ch + channel] = (int16_t)(uint16_t)kx;
+            out[(t + 1) * ch + channel] = (int16_t)(uint16_t)ky;
+        }
+    };
+    if (order_max <= 28)
+        warp_iir_quad<4>(sm.cf[q], order, order_max, io, proc, emit);
+    else if (order_max <= 56)
+        warp_iir_quad<8>(sm.cf[q], order, order_max, io, proc, emit);
+    else
+        warp_iir_quad<16>(sm.cf[q], order, order_max, io, proc, emit);
+
+    if (exists && !frame_ok) { // malformed frame: silence
+        for (int t = hl; t < kFrame; t += 8)
+            out[(size_t)t * ch + (pos < ch ? pos : 0)] = 0;
     }
 }
 

@@ -540,4 +540,101 @@ __device__ void warp_iir_synthesis_pair(const CoefSmem &cf, int order, int32_t *
         warp_iir_pair<8>(cf, order, buf, active, n, order_max);
 }
 
+// ---------------------------------------------------------------------------
+// K6, batch form: FOUR subframes per warp (quarter q = lane>>3 owns one), eight lanes x
+// TPL taps each (TPL*7 >= order, so a quarter's last lane only ever holds zero
+// coefficients and shfl_down past the quarter's edge returns its own, zero, value).
+// No shared-memory sample planes: residues arrive from global memory 16 at a time per
+// quarter (one coalesced 64-byte load, one block ahead) and are handed to lane 0 of the
+// quarter by shuffle; finished samples are parked in a 64-byte staging row per quarter
+// and leave 16 at a time.  Per 16 outputs a quarter therefore touches shared memory
+// 16 + 1 times and global memory twice.
+struct QuadIo {
+    const int32_t *res;   // this quarter's residues (global), 2048 ints, 16-byte aligned
+    int32_t *stage;       // this quarter's staging rows in shared memory: [2][16]
+};
+
+template <int TPL>
+struct QuadState {
+    uint32_t cl[TPL];
+    int32_t ch[TPL];
+    unsigned long long alo[TPL];
+    uint32_t ahi[TPL];
+    uint32_t sp;
+};
+
+// One block of 16 outputs t = 16*B + e.  WARM: bias term from the prefix table (t <= order).
+template <int TPL, bool WARM, bool FIRST>
+__device__ __forceinline__ void quad_block(QuadState<TPL> &st, const CoefSmem &cf, int order, unsigned long long steady,
+                                           int B, int2 rcur, int32_t *stage_row, bool writer)
+{
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int t = 16 * B + e;
+        const int rt = __shfl_sync(kFull, (e & 1) ? rcur.y : rcur.x, e >> 1, 8);
+        int vnext;
+        if (FIRST && e == 0) {
+            vnext = rt; // s[0] = r[0]
+        } else {
+            constexpr int kRot = 0; (void)kRot;
+            const int u = (e + 16 * TPL - 1) % TPL; // == (t - 1) % TPL, static
+#pragma unroll
+            for (int m = 0; m < TPL; m++) {
+                st.alo[(m + u) % TPL] = mad_wide_u32(st.cl[m], st.sp, st.alo[(m + u) % TPL]);
+                st.ahi[(m + u) % TPL] += (uint32_t)st.ch[m] * st.sp;
+            }
+            const unsigned long long full0 = st.alo[u] + ((unsigned long long)st.ahi[u] << 32);
+            const unsigned long long incoming = __shfl_down_sync(kFull, full0, 1, 8);
+            const unsigned long long base = WARM ? cf.pre[t < order ? t : order] : steady;
+            const unsigned long long tt = base - full0;
+            vnext = rt - (int32_t)((long long)tt >> kQ);
+            vnext = __shfl_sync(kFull, vnext, 0, 8);
+            st.alo[u] = incoming;
+            st.ahi[u] = 0;
+        }
+        if (writer)
+            stage_row[e] = vnext;
+        st.sp = (uint32_t)(vnext + kSampleBias);
+    }
+}
+
+// Runs the recurrence for the quarter's subframe; after every block calls
+// emit(B, kx, ky) with this lane's two finished samples s[16B + 2*hl], s[16B + 2*hl + 1].
+template <int TPL, typename Emit>
+__device__ void warp_iir_quad(const CoefSmem &cf, int order, int order_max, const QuadIo io, bool has_res, Emit emit)
+{
+    const int hl = lane_id() & 7;
+    QuadState<TPL> st;
+#pragma unroll
+    for (int m = 0; m < TPL; m++) {
+        const int j = TPL * hl + m; // tap j+1
+        st.cl[m] = j < 112 ? cf.clo[j] : 0u;
+        st.ch[m] = j < 112 ? cf.chi[j] : 0;
+        st.alo[m] = 0;
+        st.ahi[m] = 0;
+    }
+    st.sp = 0;
+    const unsigned long long steady = cf.pre[order];
+    const bool writer = hl == 0;
+    const int2 *r2 = reinterpret_cast<const int2 *>(io.res);
+    int2 rcur = has_res ? __ldg(r2 + hl) : make_int2(0, 0);
+    int2 rnext = has_res ? __ldg(r2 + 8 + hl) : make_int2(0, 0);
+    const int warm_blocks = order_max / 16 + 1; // blocks that contain some t <= order
+    for (int B = 0; B < kFrame / 16; B++) {
+        int32_t *row = io.stage + (B & 1) * 16;
+        if (B == 0)
+            quad_block<TPL, true, true>(st, cf, order, steady, B, rcur, row, writer);
+        else if (B < warm_blocks)
+            quad_block<TPL, true, false>(st, cf, order, steady, B, rcur, row, writer);
+        else
+            quad_block<TPL, false, false>(st, cf, order, steady, B, rcur, row, writer);
+        rcur = rnext;
+        if (B + 2 < kFrame / 16 && has_res)
+            rnext = __ldg(r2 + (B + 2) * 8 + hl);
+        __syncwarp();
+        const int2 kept = *reinterpret_cast<const int2 *>(row + 2 * hl);
+        emit(B, kept.x, kept.y);
+    }
+}
+
 } // namespace selab200

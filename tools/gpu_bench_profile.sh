@@ -11,6 +11,6 @@ cut -c1-400 gpurun_out/bench_ref_$TAG.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_bench_$TAG.log 2>&1
 tail -3 gpurun_out/launches_$TAG.csv
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_encode|k_synthesise|k_rice_decode' -s 6 -c 6 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_encode_units|k_synthesise|k_rice_decode' -s 4 -c 4 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out/

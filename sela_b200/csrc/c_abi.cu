@@ -169,6 +169,7 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     p.status = d_status;
     p.units = static_cast<UnitRecord *>(d_ws);
     p.slots = reinterpret_cast<uint32_t *>(static_cast<char *>(d_ws) + align256(n_units * sizeof(UnitRecord)));
+    p.residues = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(p.slots) + align256(n_units * (size_t)kSlotWords * 4));
     if (stereo) {
         constexpr size_t smem = encode_smem_bytes<true>();
         if (int rc = set_smem(k_encode_units<true>, smem))
@@ -359,7 +360,8 @@ size_t selab200_encode_words_bound(uint32_t n_frames, uint32_t channels)
 size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 {
     const size_t n_units = encode_units(n_frames, channels);
-    return align256(n_units * sizeof(UnitRecord)) + n_units * (size_t)kSlotWords * 4 + 256;
+    return align256(n_units * sizeof(UnitRecord)) + align256(n_units * (size_t)kSlotWords * 4) +
+           n_units * (size_t)kFrame * 4 + 256;
 }
 
 size_t selab200_decode_workspace_bytes(uint32_t n_frames, uint32_t channels)

@@ -50,6 +50,7 @@ struct EncodeParams {
     int32_t *status;
     UnitRecord *units;             // workspace [n_units]
     uint32_t *slots;               // workspace [n_units][kSlotWords]
+    int32_t *residues;             // workspace [n_units][2048]: FIR output, re-read by the Rice stages (L2-resident)
 };
 
 __host__ __device__ inline uint32_t encode_units(uint32_t n_frames, uint32_t channels)
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
     constexpr int kChan = STEREO ? 2 : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                    // [kChan][pad + 2048]
-    WarpScratch &scratch = *reinterpret_cast<WarpScratch *>(smem_raw + kChan * kRow * 2);
-    CoefSmem &cf = *reinterpret_cast<CoefSmem *>(smem_raw + kChan * kRow * 2 + sizeof(WarpScratch));
+    AnalysisScratch &scratch = *reinterpret_cast<AnalysisScratch *>(smem_raw + kChan * kRow * 2);
+    CoefSmem &cf = *reinterpret_cast<CoefSmem *>(smem_raw + kChan * kRow * 2 + sizeof(AnalysisScratch));
 
     const int lane = lane_id();
     const uint32_t unit = blockIdx.x;
@@ -101,24 +102,21 @@ __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
     __syncwarp();
 
     // ---- analysis ----
-    int32_t *res = scratch.res;
-    warp_autocorrelation(sig, scratch.a);
-    warp_schur(scratch.a);
-    const int order = warp_order_and_quantise(scratch.a, cf);
-    warp_coefficients(cf, scratch.a.t, order);
+    int32_t *res = p.residues + (size_t)unit * kFrame;
+    warp_autocorrelation(sig, scratch);
+    warp_schur(scratch);
+    const int order = warp_order_and_quantise(scratch, cf);
+    warp_coefficients(cf, scratch.t(), order);
     warp_fir_residual(sig, cf, order, res);
 
     // ---- Rice: parameter search, then pack into this unit's slot ----
-    const int32_t *qv = cf.q;
-    auto q_at = [qv](int i) { return qv[i]; };
-    auto r_at = [res](int i) { return res[i]; };
-    const RiceChoice cq = warp_rice_choose(q_at, order);
-    const RiceChoice cr = warp_rice_choose(r_at, kFrame);
+    const RiceChoice cq = warp_rice_choose(cf.q, order);
+    const RiceChoice cr = warp_rice_choose(res, kFrame);
     const bool too_large = cq.words > kSlotReflWords || cr.words > kSlotWords - kSlotReflWords;
     uint32_t *slot = p.slots + (size_t)unit * kSlotWords;
     if (!too_large) {
-        warp_rice_pack(q_at, order, cq.k, cq.words, slot);
-        warp_rice_pack(r_at, kFrame, cr.k, cr.words, slot + kSlotReflWords);
+        warp_rice_pack(cf.q, order, cq.k, cq.words, slot);
+        warp_rice_pack(res, kFrame, cr.k, cr.words, slot + kSlotReflWords);
     }
     if (lane == 0) {
         UnitRecord u;
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
 template <bool STEREO>
 constexpr size_t encode_smem_bytes()
 {
-    return (size_t)(STEREO ? 2 : 1) * (kHistoryPad + kFrame) * 2 + sizeof(WarpScratch) + sizeof(CoefSmem);
+    return (size_t)(STEREO ? 2 : 1) * (kHistoryPad + kFrame) * 2 + sizeof(AnalysisScratch) + sizeof(CoefSmem);
 }
 
 // Which unit is emitted for output subframe (frame, channel), and as what.
@@ -333,10 +331,11 @@ __global__ void k_synthesise(DecodeParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t ch = p.channels;
     int32_t *planes = reinterpret_cast<int32_t *>(smem_raw);                  // [ch][2048], by channel
-    CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(planes + (size_t)ch * kFrame);
-    double *t_all = reinterpret_cast<double *>(coef_all + ch);                // [warps][104]
+    IirSmem *iir_all = reinterpret_cast<IirSmem *>(planes + (size_t)ch * kFrame);
     const uint32_t n_warps = (ch + 1) / 2;
-    int *meta = reinterpret_cast<int *>(t_all + (size_t)n_warps * 104); // [ch] type, [ch] parent, [1] valid
+    double *t_all = reinterpret_cast<double *>(iir_all + ch);                 // [warps][104]
+    CoefSmem *coef_all = reinterpret_cast<CoefSmem *>(t_all + (size_t)n_warps * 104);
+    int *meta = reinterpret_cast<int *>(coef_all + ch); // [ch] type, [ch] parent, [1] valid
 
     const uint32_t frame = blockIdx.x;
     const int warp = warp_id(), lane = lane_id();
@@ -400,13 +399,13 @@ __global__ void k_synthesise(DecodeParams p)
             __syncwarp();
             // order 0 behaves like order 1 with a zero predictor (linear_predictor.cpp:19-22)
             warp_coefficients(cf, t_all + warp * 104, order);
-            warp_iir_prepare(cf, order);
+            warp_iir_prepare(cf, iir_all[pos], order);
         }
         const bool upper = lane >= 16;
         const uint32_t my_pos = (upper && has_b) ? pos_b : pos_a;
         const selab200_subframe_desc d = fd[my_pos];
-        warp_iir_synthesis_pair(coef_all[my_pos], d.lpc_order, planes + (size_t)d.channel * kFrame,
-                                !upper || has_b, kFrame);
+        warp_iir_synthesis_pair(coef_all[my_pos], iir_all[my_pos], d.lpc_order,
+                                planes + (size_t)d.channel * kFrame, !upper || has_b, kFrame);
     }
     __syncthreads();
 
@@ -425,8 +424,9 @@ __global__ void k_synthesise(DecodeParams p)
 // difference-coded subframes and a channel count other than 2 (the reference's encoder never
 // produces those; k_synthesise above picks them up).
 struct QuadSmem {
-    CoefSmem cf[4];
+    IirSmem ii[4];
     double t[104];
+    CoefSmem cf[4];
     int32_t stage[4][2][16];
 };
 
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
             cf.q[i] = i < order_h ? p.ws_q[(size_t)sub_h * 128 + i] : 0;
         __syncwarp();
         warp_coefficients(cf, sm.t, order_h); // order 0 behaves like a zero predictor
-        warp_iir_prepare(cf, order_h);
+        warp_iir_prepare(cf, sm.ii[h], order_h);
     }
     int order_max = order;
     order_max = max(order_max, __shfl_xor_sync(kFull, order_max, 8));
@@ -511,11 +511,11 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
         }
     };
     if (order_max <= 28)
-        warp_iir_quad<4>(sm.cf[q], order, order_max, io, proc, emit);
+        warp_iir_quad<4>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
     else if (order_max <= 56)
-        warp_iir_quad<8>(sm.cf[q], order, order_max, io, proc, emit);
+        warp_iir_quad<8>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
     else
-        warp_iir_quad<16>(sm.cf[q], order, order_max, io, proc, emit);
+        warp_iir_quad<16>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
 
     if (exists && !frame_ok) { // malformed frame: silence
         for (int t = hl; t < kFrame; t += 8)
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
 
 inline size_t synthesise_smem_bytes(uint32_t ch)
 {
-    return (size_t)ch * kFrame * 4 + ch * sizeof(CoefSmem) + ((ch + 1) / 2) * 104 * sizeof(double) +
-           (2 * ch + 1) * sizeof(int);
+    return (size_t)ch * kFrame * 4 + ch * (sizeof(CoefSmem) + sizeof(IirSmem)) +
+           ((ch + 1) / 2) * 104 * sizeof(double) + (2 * ch + 1) * sizeof(int);
 }
 
 // ------------------------------------------------------------ stage level --
@@ -535,7 +535,7 @@ inline size_t synthesise_smem_bytes(uint32_t ch)
 __global__ void __launch_bounds__(32) k_lpc_residues(const int32_t *samples, uint32_t n_sub, uint8_t *order_out,
                                                      int32_t *q_out, int32_t *residues)
 {
-    __shared__ __align__(16) WarpScratch scratch;
+    __shared__ __align__(16) AnalysisScratch scratch;
     __shared__ __align__(16) CoefSmem cf;
     __shared__ __align__(16) int32_t s_pad[kHistoryPad + kFrame];
     const uint32_t sub = blockIdx.x;
@@ -547,13 +547,11 @@ __global__ void __launch_bounds__(32) k_lpc_residues(const int32_t *samples, uin
         s[i] = samples[(size_t)sub * kFrame + i];
     __syncwarp();
     PlainSignal sig{s};
-    warp_autocorrelation(sig, scratch.a);
-    warp_schur(scratch.a);
-    const int order = warp_order_and_quantise(scratch.a, cf);
-    warp_coefficients(cf, scratch.a.t, order);
-    warp_fir_residual(sig, cf, order, scratch.res);
-    for (int i = lane; i < kFrame; i += 32)
-        residues[(size_t)sub * kFrame + i] = scratch.res[i];
+    warp_autocorrelation(sig, scratch);
+    warp_schur(scratch);
+    const int order = warp_order_and_quantise(scratch, cf);
+    warp_coefficients(cf, scratch.t(), order);
+    warp_fir_residual(sig, cf, order, residues + (size_t)sub * kFrame);
     for (int i = lane; i < kMaxOrder; i += 32)
         q_out[(size_t)sub * kMaxOrder + i] = i < order ? cf.q[i] : 0;
     if (lane == 0)
@@ -565,6 +563,7 @@ __global__ void __launch_bounds__(32) k_lpc_samples(const int32_t *residues, uin
                                                     const int32_t *q_in, int32_t *samples)
 {
     __shared__ __align__(16) CoefSmem cf;
+    __shared__ __align__(16) IirSmem ii;
     __shared__ double t[104];
     __shared__ __align__(16) int32_t buf[kFrame];
     const uint32_t sub = blockIdx.x;
@@ -578,8 +577,8 @@ __global__ void __launch_bounds__(32) k_lpc_samples(const int32_t *residues, uin
         buf[i] = residues[(size_t)sub * kFrame + i];
     __syncwarp();
     warp_coefficients(cf, t, order);
-    warp_iir_prepare(cf, order);
-    warp_iir_synthesis_pair(cf, order, buf, lane < 16, kFrame); // upper half shadows, never stores
+    warp_iir_prepare(cf, ii, order);
+    warp_iir_synthesis_pair(cf, ii, order, buf, lane < 16, kFrame); // upper half shadows, never stores
     for (int i = lane; i < kFrame; i += 32)
         samples[(size_t)sub * kFrame + i] = buf[i];
 }
@@ -602,8 +601,7 @@ __global__ void __launch_bounds__(32) k_rice_encode(const int32_t *values, const
     const uint32_t st = blockIdx.x;
     const int32_t *v = values + (size_t)st * stride;
     const int n = (int)counts[st];
-    auto at = [v](int i) { return v[i]; };
-    RiceChoice c = warp_rice_choose(at, n);
+    RiceChoice c = warp_rice_choose(v, n);
     if (lane_id() == 0) {
         k_out[st] = c.k;
         n_words_out[st] = c.words;
@@ -613,7 +611,7 @@ __global__ void __launch_bounds__(32) k_rice_encode(const int32_t *values, const
             raise_status(status, SELAB200_ERR_CAPACITY);
         return;
     }
-    warp_rice_pack(at, n, c.k, c.words, words + (size_t)st * words_stride);
+    warp_rice_pack(v, n, c.k, c.words, words + (size_t)st * words_stride);
 }
 
 // rice::RiceDecoder::process, one stream per lane.

@@ -13,34 +13,37 @@ namespace selab200 {
 
 // Per-warp shared memory.  The predictor (shared by encoder and decoder):
 struct CoefSmem {
-    long long c[104];            // Q35 coefficients c[0..order], zero above
-    uint32_t clo[112];           // low / high words of c[1..], tap j at index j-1, zero padded:
-    int32_t  chi[112];           //   the FIR / IIR read them in blocks of 8
-    unsigned long long pre[104]; // IIR warm-up: 2^34 + BIAS * sum_{j<=t} c[j]   (t = 0..order)
-    int32_t q[104];              // quantised reflection coefficients
+    uint32_t clo[112];           // low / high words of the Q35 coefficients c[1..], tap j at index
+    int32_t  chi[112];           //   j-1, zero padded: the FIR / IIR read them in blocks of 8
+    int32_t  q[104];             // quantised reflection coefficients
 };
-// Analysis scratch; dead once the predictor exists, so it shares its bytes with the
-// residual buffer the FIR fills afterwards.
+// Decoder only: warm-up bias table of the IIR, 2^34 + 2^17 * sum_{j<=t} c[j]  (t = 0..order)
+struct IirSmem {
+    unsigned long long pre[104];
+};
+// Analysis scratch (3 KB).  The ring is dead once the autocorrelation is done; the
+// reflection coefficients (kk) and the step-up row (t) then live in its bytes.
 struct AnalysisScratch {
-    double ring[512]; // x tile for the mean pass, then the d = x - mean ring (swizzled)
+    double ring[256]; // x tile for the mean pass, then the d = x - mean ring (swizzled)
     double ac[128];   // autocorrelation (raw, then normalised)
-    double kk[104];   // reflection coefficients k[0..99]
-    double t[104];    // step-up scratch
+    __device__ __forceinline__ double *kk() { return ring; }        // k[0..99]
+    __device__ __forceinline__ double *t() { return ring + 104; }   // step-up scratch [0..99]
 };
-union WarpScratch {
-    AnalysisScratch a;
-    int32_t res[kFrame];
-};
-static_assert(sizeof(AnalysisScratch) <= sizeof(int32_t) * kFrame, "analysis scratch must fit under the residuals");
 using LpcSmem = AnalysisScratch;
 
+__device__ __forceinline__ long long coef_at(const CoefSmem &cf, int j) // c[j], j >= 1
+{
+    return (long long)(((unsigned long long)(uint32_t)cf.chi[j - 1] << 32) | cf.clo[j - 1]);
+}
+
 // ---------------------------------------------------------------------------
-// ring addressing: 512 doubles = 256 chunks of 16 B.  Odd 128-byte rows have
-// their chunk pairs swapped so that the "own window" LDS.128 of the
-// autocorrelation (lanes 32 B apart) is bank-conflict free.
+// ring addressing: 256 doubles = 128 chunks of 16 B (a 128-sample tile plus the 127
+// samples of history the furthest lane still needs).  Odd 128-byte rows have their
+// chunk pairs swapped so that the "own window" LDS.128 of the autocorrelation (lanes
+// 32 B apart) is bank-conflict free.
 __device__ __forceinline__ int ring_chunk(int chunk)
 {
-    chunk &= 255;
+    chunk &= 127;
     return chunk ^ ((chunk >> 3) & 1);
 }
 __device__ __forceinline__ int ring_index(int p) // logical sample index (may be negative)
@@ -101,11 +104,11 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
     const double mean = ddiv(sum, (double)kFrame); // exact: power of two
 
     // ---- autocorrelation ----
-    // logical d[-128..-1] = 0  -> chunks 192..255
+    // logical d[-128..-1] = 0  -> chunks 64..127 (the upper half of the ring)
     {
         double2 *r2 = reinterpret_cast<double2 *>(sm.ring);
-        r2[192 + lane] = make_double2(0.0, 0.0);
-        r2[224 + lane] = make_double2(0.0, 0.0);
+        r2[64 + lane] = make_double2(0.0, 0.0);
+        r2[96 + lane] = make_double2(0.0, 0.0);
     }
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     double p1 = 0.0, p2 = 0.0, p3 = 0.0; // d[4G-1], d[4G-2], d[4G-3]
@@ -113,7 +116,7 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
     // Groups are processed 8 at a time (g = g0 + i, g0 a multiple of 8), which makes the
     // swizzle bit of every access loop-invariant: for the broadcast group it is (i>>2)&1, a
     // compile-time constant; for the lane's own group G = g - lane it is ((i - lane)>>2)&1.
-    // The physical byte offset of chunk 2G is then (32*g0 + own_off[i]) & 4095.
+    // The physical byte offset of chunk 2G is then (32*g0 + own_off[i]) & 2047.
     int own_off[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -121,20 +124,20 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
         own_off[i] = 16 * (2 * rel + ((rel >> 2) & 1));
     }
 
-    for (int tile = 0; tile < kFrame / 256; tile++) {
+    for (int tile = 0; tile < kFrame / 128; tile++) {
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            int j = tile * 256 + r * 32 + lane;
+        for (int r = 0; r < 4; r++) {
+            int j = tile * 128 + r * 32 + lane;
             sm.ring[ring_index(j)] = dsub(sample_to_x(sig.at(j)), mean);
         }
         __syncwarp();
-        for (int blk = 0; blk < 8; blk++) {
-            const int gb = (tile * 64 + blk * 8) * 32; // byte offset of chunk 2*g0 before wrapping
-            const char *bbase = ringb + (gb & 4095);    // 256-byte aligned: the 8 broadcast groups never wrap
+        for (int blk = 0; blk < 4; blk++) {
+            const int gb = (tile * 32 + blk * 8) * 32; // byte offset of chunk 2*g0 before wrapping
+            const char *bbase = ringb + (gb & 2047);    // 256-byte aligned: the 8 broadcast groups never wrap
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int oo = (gb + own_off[i]) & 4095;
+                const int oo = (gb + own_off[i]) & 2047;
                 const double2 o0 = *reinterpret_cast<const double2 *>(ringb + oo);
                 const double2 o1 = *reinterpret_cast<const double2 *>(ringb + (oo ^ 16));
                 constexpr int kSw[8] = {0, 0, 0, 0, 16, 16, 16, 16};
@@ -195,6 +198,7 @@ __device__ void warp_autocorrelation(const Sig &sig, LpcSmem &sm)
 __device__ void warp_schur(LpcSmem &sm)
 {
     const int lane = lane_id();
+    double *kk = sm.kk(); // overlays the ring, which the autocorrelation no longer needs
     double g0[4], g1[4];
 #pragma unroll
     for (int m = 0; m < 4; m++) {
@@ -208,7 +212,7 @@ __device__ void warp_schur(LpcSmem &sm)
     double k = ddiv(-head, err);
     err = dadd(err, dmul(head, k));
     if (lane == 0)
-        sm.kk[0] = k;
+        kk[0] = k;
     for (int i = 1; i < kMaxOrder; i++) {
         const double kp = k;
         const double nxt = shfl_down_d(g1[0], 1); // g1[4(l+1)] of the previous sweep
@@ -224,7 +228,7 @@ __device__ void warp_schur(LpcSmem &sm)
         k = ddiv(-head, err);
         err = dadd(err, dmul(head, k));
         if (lane == 0)
-            sm.kk[i] = k;
+            kk[i] = k;
     }
     __syncwarp();
 }
@@ -232,14 +236,15 @@ __device__ void warp_schur(LpcSmem &sm)
 // ---------------------------------------------------------------------------
 // K2b: order selection + 7-bit quantisation
 // generateoptimalLpcOrder / quantizeReflectionCoefficients (residue_generator.cpp:70-96).
-__device__ int warp_order_and_quantise(const LpcSmem &sm, CoefSmem &cf)
+__device__ int warp_order_and_quantise(LpcSmem &sm, CoefSmem &cf)
 {
     const int lane = lane_id();
+    const double *kk = sm.kk();
     int best = -1;
 #pragma unroll
     for (int t = 0; t < 4; t++) {
         int i = lane + 32 * t;
-        if (i < kMaxOrder && fabs(sm.kk[i]) > 0.05)
+        if (i < kMaxOrder && fabs(kk[i]) > 0.05)
             best = i;
     }
     best = __reduce_max_sync(kFull, best);
@@ -250,7 +255,7 @@ __device__ int warp_order_and_quantise(const LpcSmem &sm, CoefSmem &cf)
     for (int t = 0; t < 4; t++) {
         int i = lane + 32 * t;
         if (i < order) {
-            double kv = sm.kk[i];
+            double kv = kk[i];
             double v;
             if (i == 0)
                 v = floor(dmul(64.0, dadd(-1.0, dmul(sqrt2, dsqrt(dadd(kv, 1.0))))));
@@ -268,7 +273,7 @@ __device__ int warp_order_and_quantise(const LpcSmem &sm, CoefSmem &cf)
 }
 
 // ---------------------------------------------------------------------------
-// K2c: de-quantise + step-up -> Q35 integer predictor in sm.c[0..order]
+// K2c: de-quantise + step-up -> Q35 integer predictor (cf.clo/chi, tap j at index j-1)
 // LinearPredictor::dequantizeReflectionCoefficients / generatelinearPredictionCoefficients
 // (src/lpc/linear_predictor.cpp:16-61).  Shared by encoder and decoder.
 // Table indices are clamped to [0,127] (the reference reads out of bounds there).
@@ -290,8 +295,6 @@ __device__ void warp_coefficients(CoefSmem &cf, double *t, int order)
     for (int i = lane; i < 112; i += 32) {
         cf.clo[i] = 0;
         cf.chi[i] = 0;
-        if (i < 104)
-            cf.c[i] = 0;
     }
     __syncwarp();
     if (order <= 1)
@@ -317,7 +320,6 @@ __device__ void warp_coefficients(CoefSmem &cf, double *t, int order)
     const double scale = 34359738368.0; // 2^35
     for (int m = lane; m < order; m += 32) {
         const long long v = __double2ll_rz(dmul(scale, -t[m]));
-        cf.c[1 + m] = v;
         cf.clo[m] = (uint32_t)v;
         cf.chi[m] = (int32_t)(v >> 32);
     }
@@ -345,7 +347,7 @@ __device__ void warp_fir_residual(const Sig &sig, const CoefSmem &cf, int order,
     const int nblk = (order + 7) >> 3;
     long long csum = 0;
     for (int j = lane + 1; j <= order; j += 32)
-        csum += cf.c[j];
+        csum += coef_at(cf, j);
     csum = (long long)warp_sum_u64((unsigned long long)csum);
     const unsigned long long corr = (1ull << (kQ - 1)) - ((unsigned long long)csum << 17);
     const uint4 *clo4 = reinterpret_cast<const uint4 *>(cf.clo);
@@ -410,7 +412,7 @@ __device__ void warp_fir_residual(const Sig &sig, const CoefSmem &cf, int order,
 // broadcasts it, and every accumulator moves one tap down (one 64-bit shuffle per
 // lane, register renaming inside a lane).  Critical path per sample: one IMAD, a
 // 64-bit subtract, a shift and ONE shuffle -- instead of a five-level reduction.
-__device__ void warp_iir_prepare(CoefSmem &cf, int order)
+__device__ void warp_iir_prepare(const CoefSmem &cf, IirSmem &ii, int order)
 {
     // pre[t] = 2^34 + 2^17 * sum_{j=1..t} c[j]: removes the sample bias for output t
     // (during warm-up only taps j <= t have seen a real sample)
@@ -419,7 +421,7 @@ __device__ void warp_iir_prepare(CoefSmem &cf, int order)
 #pragma unroll
     for (int m = 0; m < 4; m++) {
         const int j = 4 * lane + m + 1;
-        run += (j <= order) ? cf.c[j] : 0;
+        run += (j <= order && j <= 112) ? coef_at(cf, j) : 0;
         v[m] = run;
     }
     unsigned long long incl = (unsigned long long)run;
@@ -434,10 +436,10 @@ __device__ void warp_iir_prepare(CoefSmem &cf, int order)
     for (int m = 0; m < 4; m++) {
         const int j = 4 * lane + m + 1;
         if (j < 104)
-            cf.pre[j] = (1ull << (kQ - 1)) + ((excl + (unsigned long long)v[m]) << 17);
+            ii.pre[j] = (1ull << (kQ - 1)) + ((excl + (unsigned long long)v[m]) << 17);
     }
     if (lane == 0)
-        cf.pre[0] = 1ull << (kQ - 1);
+        ii.pre[0] = 1ull << (kQ - 1);
     __syncwarp();
 }
 
@@ -447,7 +449,7 @@ __device__ void warp_iir_prepare(CoefSmem &cf, int order)
 // returns the lane's own, zero, value: no special case).  Per step the warp issues
 // 2*TPL IMADs + ~14 bookkeeping instructions for TWO samples.
 template <int TPL>
-__device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool active, int n, int order_max)
+__device__ void warp_iir_pair(const CoefSmem &cf, const IirSmem &ii, int order, int32_t *buf, bool active, int n, int order_max)
 {
     const int hl = lane_id() & 15;
     uint32_t cl[TPL];
@@ -467,7 +469,7 @@ __device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool 
         alo[m] = 0;
         ahi[m] = 0;
     }
-    const unsigned long long steady = cf.pre[order];
+    const unsigned long long steady = ii.pre[order];
     uint32_t sp = (uint32_t)(buf[0] + kSampleBias); // s[0] = r[0]
     const bool writer = active && hl == 0;
     // step(u, i, base): consumes s'[i] in `sp`, produces s[i+1].  Slot m of this step
@@ -500,7 +502,7 @@ __device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool 
         for (int u = 0; u < TPL; u++) {
             if (i < last) {
                 const int t = i + 1;
-                const unsigned long long base = cf.pre[t < order ? t : order];
+                const unsigned long long base = ii.pre[t < order ? t : order];
                 SELAB200_IIR_STEP(u, i, base);
                 i++;
             }
@@ -528,16 +530,16 @@ __device__ void warp_iir_pair(const CoefSmem &cf, int order, int32_t *buf, bool 
 // Synthesis of two subframes in one warp.  cf/buf/order/active are PER HALF (lanes
 // 0-15: A, lanes 16-31: B); cf.pre must be ready (warp_iir_prepare).  buf: r on entry,
 // s on exit (in place), n samples.  An inactive half computes but never stores.
-__device__ void warp_iir_synthesis_pair(const CoefSmem &cf, int order, int32_t *buf, bool active, int n)
+__device__ void warp_iir_synthesis_pair(const CoefSmem &cf, const IirSmem &ii, int order, int32_t *buf, bool active, int n)
 {
     const int other = __shfl_xor_sync(kFull, order, 16);
     const int order_max = order > other ? order : other;
     if (order_max <= 30)
-        warp_iir_pair<2>(cf, order, buf, active, n, order_max);
+        warp_iir_pair<2>(cf, ii, order, buf, active, n, order_max);
     else if (order_max <= 60)
-        warp_iir_pair<4>(cf, order, buf, active, n, order_max);
+        warp_iir_pair<4>(cf, ii, order, buf, active, n, order_max);
     else
-        warp_iir_pair<8>(cf, order, buf, active, n, order_max);
+        warp_iir_pair<8>(cf, ii, order, buf, active, n, order_max);
 }
 
 // ---------------------------------------------------------------------------
@@ -564,8 +566,8 @@ struct QuadState {
 };
 
 // One block of 16 outputs t = 16*B + e.  WARM: bias term from the prefix table (t <= order).
-template <int TPL, bool WARM, bool FIRST>
-__device__ __forceinline__ void quad_block(QuadState<TPL> &st, const CoefSmem &cf, int order, unsigned long long steady,
+template <int TPL, bool WARM>
+__device__ __forceinline__ void quad_block(QuadState<TPL> &st, const IirSmem &ii, int order, unsigned long long steady,
                                            int B, int2 rcur, int32_t *stage_row, bool writer)
 {
 #pragma unroll
@@ -573,10 +575,9 @@ __device__ __forceinline__ void quad_block(QuadState<TPL> &st, const CoefSmem &c
         const int t = 16 * B + e;
         const int rt = __shfl_sync(kFull, (e & 1) ? rcur.y : rcur.x, e >> 1, 8);
         int vnext;
-        if (FIRST && e == 0) {
+        if (WARM && e == 0 && B == 0) { // uniform branch, only compiled into the warm-up variant
             vnext = rt; // s[0] = r[0]
         } else {
-            constexpr int kRot = 0; (void)kRot;
             const int u = (e + 16 * TPL - 1) % TPL; // == (t - 1) % TPL, static
 #pragma unroll
             for (int m = 0; m < TPL; m++) {
@@ -585,7 +586,7 @@ __device__ __forceinline__ void quad_block(QuadState<TPL> &st, const CoefSmem &c
             }
             const unsigned long long full0 = st.alo[u] + ((unsigned long long)st.ahi[u] << 32);
             const unsigned long long incoming = __shfl_down_sync(kFull, full0, 1, 8);
-            const unsigned long long base = WARM ? cf.pre[t < order ? t : order] : steady;
+            const unsigned long long base = WARM ? ii.pre[t < order ? t : order] : steady;
             const unsigned long long tt = base - full0;
             vnext = rt - (int32_t)((long long)tt >> kQ);
             vnext = __shfl_sync(kFull, vnext, 0, 8);
@@ -601,7 +602,7 @@ __device__ __forceinline__ void quad_block(QuadState<TPL> &st, const CoefSmem &c
 // Runs the recurrence for the quarter's subframe; after every block calls
 // emit(B, kx, ky) with this lane's two finished samples s[16B + 2*hl], s[16B + 2*hl + 1].
 template <int TPL, typename Emit>
-__device__ void warp_iir_quad(const CoefSmem &cf, int order, int order_max, const QuadIo io, bool has_res, Emit emit)
+__device__ void warp_iir_quad(const CoefSmem &cf, const IirSmem &ii, int order, int order_max, const QuadIo io, bool has_res, Emit emit)
 {
     const int hl = lane_id() & 7;
     QuadState<TPL> st;
@@ -614,7 +615,7 @@ __device__ void warp_iir_quad(const CoefSmem &cf, int order, int order_max, cons
         st.ahi[m] = 0;
     }
     st.sp = 0;
-    const unsigned long long steady = cf.pre[order];
+    const unsigned long long steady = ii.pre[order];
     const bool writer = hl == 0;
     const int2 *r2 = reinterpret_cast<const int2 *>(io.res);
     int2 rcur = has_res ? __ldg(r2 + hl) : make_int2(0, 0);
@@ -622,12 +623,10 @@ __device__ void warp_iir_quad(const CoefSmem &cf, int order, int order_max, cons
     const int warm_blocks = order_max / 16 + 1; // blocks that contain some t <= order
     for (int B = 0; B < kFrame / 16; B++) {
         int32_t *row = io.stage + (B & 1) * 16;
-        if (B == 0)
-            quad_block<TPL, true, true>(st, cf, order, steady, B, rcur, row, writer);
-        else if (B < warm_blocks)
-            quad_block<TPL, true, false>(st, cf, order, steady, B, rcur, row, writer);
+        if (B < warm_blocks)
+            quad_block<TPL, true>(st, ii, order, steady, B, rcur, row, writer);
         else
-            quad_block<TPL, false, false>(st, cf, order, steady, B, rcur, row, writer);
+            quad_block<TPL, false>(st, ii, order, steady, B, rcur, row, writer);
         rcur = rnext;
         if (B + 2 < kFrame / 16 && has_res)
             rnext = __ldg(r2 + (B + 2) * 8 + hl);

@@ -43,14 +43,63 @@ __device__ __forceinline__ void csa(uint32_t &hi, uint32_t &lo, uint32_t a, uint
     lo = u ^ c;
 }
 
-__device__ __forceinline__ RiceChoice rice_choice_from_sums(const unsigned long long (&sums)[kMaxRice], int n)
+// vals: int32 values in shared or global memory (generic pointer), n <= 2048.  Deliberately
+// NOT inlined and written as compact loops: the encoder kernel is instruction-fetch bound
+// (81 KB of code, 16 warps in different phases per SM), so straight-line code that runs once
+// costs more in I-cache misses than it saves in issue slots.
+__device__ __noinline__ RiceChoice warp_rice_choose(const int32_t *vals, int n)
 {
-    unsigned long long best = ~0ull;
-    uint32_t best_k = 0;
+    const int lane = lane_id();
+    // bit planes of weight 1, 2, 4, 8 (carry-save side) and 16, 32, 64 (ripple side)
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, p16 = 0, p32 = 0, p64 = 0;
+    unsigned long long top = 0; // sum of u >> 19
+    const int per_lane = (n + 31) >> 5;
+    const int n_blocks = (per_lane + 15) >> 4;
+#pragma unroll 1
+    for (int blk = 0; blk < n_blocks; blk++) {
+        uint32_t w[16];
 #pragma unroll
-    for (int k = 0; k < kMaxRice; k++) {
-        const unsigned long long total = sums[k] + (unsigned long long)n * (1 + k);
-        if (total < best) {
+        for (int t = 0; t < 16; t++) {
+            const int i = lane + 32 * (blk * 16 + t);
+            const uint32_t u = i < n ? zigzag(vals[i]) : 0u;
+            top += u >> (kMaxRice - 1);
+            w[t] = u & ((1u << (kMaxRice - 1)) - 1);
+        }
+        uint32_t e8[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            uint32_t f4[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int t = b * 8 + c * 4;
+                uint32_t ta, tb;
+                csa(ta, ones, ones, w[t], w[t + 1]);
+                csa(tb, ones, ones, w[t + 2], w[t + 3]);
+                csa(f4[c], twos, twos, ta, tb);
+            }
+            csa(e8[b], fours, fours, f4[0], f4[1]);
+        }
+        uint32_t c16;
+        csa(c16, eights, eights, e8[0], e8[1]);
+        const uint32_t c32 = p16 & c16; // ripple the weight-16 carry into the upper planes
+        p16 ^= c16;
+        const uint32_t c64 = p32 & c32;
+        p32 ^= c32;
+        p64 ^= c64;
+    }
+    const uint32_t planes[7] = {ones, twos, fours, eights, p16, p32, p64};
+    unsigned long long s_k = warp_sum_u64(top);                            // S_19
+    unsigned long long best = s_k + (unsigned long long)n * kMaxRice;      // k = 19
+    uint32_t best_k = kMaxRice - 1;
+#pragma unroll 1
+    for (int k = kMaxRice - 2; k >= 0; k--) {
+        uint32_t count = 0;
+#pragma unroll
+        for (int p = 0; p < 7; p++)
+            count += (uint32_t)__popc(__ballot_sync(kFull, (planes[p] >> k) & 1u)) << p;
+        s_k = 2 * s_k + count;
+        const unsigned long long total = s_k + (unsigned long long)n * (1 + k);
+        if (total <= best) { // descending k with <= keeps the FIRST (lowest) arg-min
             best = total;
             best_k = k;
         }
@@ -58,75 +107,9 @@ __device__ __forceinline__ RiceChoice rice_choice_from_sums(const unsigned long 
     RiceChoice c;
     c.k = best_k;
     c.bits = best > 0xffffffffull ? 0xffffffffu : (uint32_t)best;
-    const unsigned long long w = (best + 31) >> 5;
-    c.words = w > 0xffffffffull ? 0xffffffffu : (uint32_t)w;
+    const unsigned long long wds = (best + 31) >> 5;
+    c.words = wds > 0xffffffffull ? 0xffffffffu : (uint32_t)wds;
     return c;
-}
-
-template <typename Val>
-__device__ RiceChoice warp_rice_choose(const Val &val, int n)
-{
-    const int lane = lane_id();
-    unsigned long long sums[kMaxRice];
-    if (n <= 256) {
-        // short streams (the reflection coefficients): direct accumulation
-#pragma unroll
-        for (int k = 0; k < kMaxRice; k++)
-            sums[k] = 0;
-        for (int i = lane; i < n; i += 32) {
-            const uint32_t u = zigzag(val(i));
-#pragma unroll
-            for (int k = 0; k < kMaxRice; k++)
-                sums[k] += u >> k;
-        }
-#pragma unroll
-        for (int k = 0; k < kMaxRice; k++)
-            sums[k] = warp_sum_u64(sums[k]);
-        return rice_choice_from_sums(sums, n);
-    }
-    // bit planes of weight 1, 2, 4, ..., 64 over this lane's (up to) 64 words
-    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, sixteens = 0, thirtytwos = 0;
-    uint32_t s16[4];
-    unsigned long long top = 0; // sum of u >> 19
-    auto word = [&](int t) -> uint32_t {
-        const int i = lane + 32 * t;
-        const uint32_t u = i < n ? zigzag(val(i)) : 0u;
-        top += u >> (kMaxRice - 1);
-        return u & ((1u << (kMaxRice - 1)) - 1);
-    };
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        uint32_t e8[2];
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
-            uint32_t f4[2];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int t = a * 16 + b * 8 + c * 4;
-                uint32_t ta, tb;
-                csa(ta, ones, ones, word(t), word(t + 1));
-                csa(tb, ones, ones, word(t + 2), word(t + 3));
-                csa(f4[c], twos, twos, ta, tb);
-            }
-            csa(e8[b], fours, fours, f4[0], f4[1]);
-        }
-        csa(s16[a], eights, eights, e8[0], e8[1]);
-    }
-    uint32_t x32, y32, sixtyfours;
-    csa(x32, sixteens, sixteens, s16[0], s16[1]);
-    csa(y32, sixteens, sixteens, s16[2], s16[3]);
-    csa(sixtyfours, thirtytwos, thirtytwos, x32, y32);
-    const uint32_t planes[7] = {ones, twos, fours, eights, sixteens, thirtytwos, sixtyfours};
-    sums[kMaxRice - 1] = warp_sum_u64(top);
-#pragma unroll
-    for (int k = kMaxRice - 2; k >= 0; k--) {
-        uint32_t count = 0;
-#pragma unroll
-        for (int p = 0; p < 7; p++)
-            count += (uint32_t)__popc(__ballot_sync(kFull, (planes[p] >> k) & 1u)) << p;
-        sums[k] = 2 * sums[k + 1] + count;
-    }
-    return rice_choice_from_sums(sums, n);
 }
 
 // generateEncodedBits + writeInts (rice_encoder.cpp:35-71).  Lane l codes the
@@ -134,8 +117,9 @@ __device__ RiceChoice warp_rice_choose(const Val &val, int n)
 // each lane its first bit.  Words wholly inside a lane's range are plain stores;
 // the (at most two) words it shares with a neighbour are OR-ed into the
 // pre-zeroed destination.  dst: `words` uint32 in global memory.
-template <typename Val>
-__device__ void warp_rice_pack(const Val &val, int n, uint32_t k, uint32_t words, uint32_t *dst)
+// A symbol is emitted as pieces of at most 32 bits (runs of ones, then "0 + payload")
+// through ONE staging/flush site -- compact code, see warp_rice_choose.
+__device__ __noinline__ void warp_rice_pack(const int32_t *vals, int n, uint32_t k, uint32_t words, uint32_t *dst)
 {
     const int lane = lane_id();
     for (uint32_t w = lane; w < words; w += 32)
@@ -147,56 +131,54 @@ __device__ void warp_rice_pack(const Val &val, int n, uint32_t k, uint32_t words
     const int hi = lo + per < n ? lo + per : n;
     uint32_t my_bits = 0;
     for (int i = lo; i < hi; i++)
-        my_bits += (zigzag(val(i)) >> k) + 1 + k;
+        my_bits += (zigzag(vals[i]) >> k) + 1 + k;
     const uint32_t end = warp_scan_inclusive_u32(my_bits);
     const uint32_t start = end - my_bits;
 
-    // 64-bit staging: bits [0, fill) of `stage` are pending for word index `widx`
+    // 64-bit staging: bits [0, fill) of `stage` are pending for word index `widx`; fill < 32
     unsigned long long stage = 0;
     uint32_t fill = start & 31;
     uint32_t widx = start >> 5;
-    auto flush = [&](uint32_t value) {
-        const uint32_t b0 = widx << 5;
-        if (b0 >= start && b0 + 32 <= end)
-            dst[widx] = value;
-        else if (value)
-            atomicOr(&dst[widx], value);
-        widx++;
-    };
     for (int i = lo; i < hi; i++) {
-        const uint32_t u = zigzag(val(i));
+        const uint32_t u = zigzag(vals[i]);
         uint32_t ones = u >> k;
-        while (ones >= 32) { // long unary run: 32 ones at a time
-            stage |= 0xffffffffull << fill;
-            flush((uint32_t)stage);
-            stage >>= 32;
-            ones -= 32;
-        }
-        // remaining ones (< 32), the zero, then k payload bits MSB first == the
-        // bit-reversed low k bits placed LSB first after the zero
-        unsigned long long code = (1ull << ones) - 1;
-        const uint32_t payload = k ? (__brev(u) >> (32 - k)) : 0u; // brev of low k bits
-        code |= (unsigned long long)payload << (ones + 1);
-        const uint32_t len = ones + 1 + k; // <= 31 + 1 + 19
-        stage |= code << fill;             // fill < 32, len <= 51: may exceed 64 bits
-        const uint32_t total = fill + len;
-        if (total >= 32) {
-            flush((uint32_t)stage);
-            if (total >= 64) {
-                flush((uint32_t)(stage >> 32));
-                // bits of `code` that did not fit: code >> (64 - fill)
-                stage = fill ? (code >> (64 - fill)) : 0ull;
-                fill = total - 64;
+        // "0 then the k payload bits MSB first" == bit-reversed low k bits, LSB first, after a zero
+        const uint32_t tail = (k ? (__brev(u) >> (32 - k)) : 0u) << 1;
+        bool last;
+        do {
+            uint32_t bits, len;
+            last = ones == 0;
+            if (ones >= 32) {
+                bits = 0xffffffffu;
+                len = 32;
+            } else if (ones) {
+                bits = (1u << ones) - 1;
+                len = ones;
             } else {
-                stage >>= 32;
-                fill = total - 32;
+                bits = tail;
+                len = 1 + k;
             }
-        } else {
-            fill = total;
-        }
+            ones -= last ? 0 : len;
+            stage |= (unsigned long long)bits << fill;
+            fill += len;
+            if (fill >= 32) {
+                const uint32_t value = (uint32_t)stage;
+                const uint32_t b0 = widx << 5;
+                if (b0 >= start && b0 + 32 <= end)
+                    dst[widx] = value;
+                else if (value)
+                    atomicOr(&dst[widx], value);
+                widx++;
+                stage >>= 32;
+                fill -= 32;
+            }
+        } while (!last);
     }
-    if (fill && hi > lo)
-        flush((uint32_t)stage);
+    if (fill && hi > lo) {
+        const uint32_t value = (uint32_t)stage;
+        if (value)
+            atomicOr(&dst[widx], value);
+    }
     __syncwarp();
 }
 

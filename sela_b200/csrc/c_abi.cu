@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -90,9 +91,22 @@ struct PipelineDrain {
 
 // Chunking of the pipelined host-buffer calls: enough chunks to overlap PCIe with compute,
 // each still several waves of warps, workspace bounded for huge batches.
-uint32_t chunk_frames_for(uint32_t n_frames)
+// `parts`: target number of chunks.  Measured on the BASELINE batch (12 919 stereo frames,
+// tools/e2e_chunk_sweep.py): encode is best at 8 chunks (4.2 ms end to end vs 3.8 ms of kernels);
+// decode at 4 -- its Rice kernel is one lane per stream and latency-bound, so a chunk must still be
+// thousands of streams.
+uint32_t chunk_frames_for(uint32_t n_frames, uint32_t parts)
 {
-    uint32_t c = (n_frames + 7) / 8;
+    if (const char *env = std::getenv("SELAB200_CHUNK_FRAMES")) { // tuning / tests only
+        long v = std::atol(env);
+        if (v > 0) {
+            uint32_t c = (uint32_t)v;
+            while ((n_frames + c - 1) / c > (uint32_t)kMaxChunks)
+                c *= 2;
+            return c;
+        }
+    }
+    uint32_t c = (n_frames + parts - 1) / parts;
     if (c < 512) c = 512;
     if (c > 16384) c = 16384;
     while ((n_frames + c - 1) / c > (uint32_t)kMaxChunks)
@@ -420,7 +434,7 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
     if (n_frames == 0)
         return 0;
     PipelineDrain drain;
-    const uint32_t cf = chunk_frames_for(n_frames);
+    const uint32_t cf = chunk_frames_for(n_frames, 8);
     const uint32_t n_chunks = (n_frames + cf - 1) / cf;
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
@@ -492,7 +506,7 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
     if (n_frames == 0)
         return 0;
     PipelineDrain drain;
-    const uint32_t cf = chunk_frames_for(n_frames);
+    const uint32_t cf = chunk_frames_for(n_frames, 4);
     const uint32_t n_chunks = (n_frames + cf - 1) / cf;
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;

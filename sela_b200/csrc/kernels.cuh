@@ -291,7 +291,7 @@ struct DecodeParams {
 constexpr int kRiceWarps = 2;
 __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p, int which)
 {
-    __shared__ uint32_t ring[kRiceWarps][kRiceRingWords * 32];
+    __shared__ uint32_t ring[kRiceWarps][kRiceRingRows * 32];
     const uint32_t sub = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_sub = p.n_frames * p.channels;
     RiceLaneStream st;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
     const uint32_t *words, const uint32_t *n_words, uint32_t words_stride, const uint32_t *k,
     const uint32_t *counts, uint32_t n_streams, int32_t *out, uint32_t out_stride, int32_t *status)
 {
-    __shared__ uint32_t ring[kRiceWarps][kRiceRingWords * 32];
+    __shared__ uint32_t ring[kRiceWarps][kRiceRingRows * 32];
     const uint32_t st_i = blockIdx.x * blockDim.x + threadIdx.x;
     RiceLaneStream st;
     st.src = words;

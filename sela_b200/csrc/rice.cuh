@@ -198,7 +198,8 @@ struct RiceLaneStream {
     uint32_t n_words, k, count;
     int32_t *out;
 };
-constexpr int kRiceRingWords = 128; // per lane; ring is [128][32] uint32 = 16 KB per warp
+constexpr int kRiceRingWords = 128; // per lane
+constexpr int kRiceRingRows = kRiceRingWords + 1; // row 128 mirrors row 0, so word w+1 is always one row below word w
 
 // Returns (per lane) false if the stream needed more bits than n_words holds.
 __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
@@ -215,6 +216,8 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
         const uint32_t v1 = w1 < nw ? __ldg(src + w1) : 0u;
         ring[(w0 & 127) * 32 + owner] = v0; // column write: 32-way bank conflict, off the parsers' path
         ring[(w1 & 127) * 32 + owner] = v1;
+        if ((w0 & 127) == 0)
+            ring[128 * 32 + owner] = v0;    // the mirror row
         if (lane == owner)
             next_block++;
     };
@@ -224,58 +227,59 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
     }
     __syncwarp();
 
+    const uint32_t *rb = ring + lane;
     uint32_t pos = 0, i = 0, q_acc = 0;
-    const uint32_t k = st.k;
-    bool done = st.count == 0;
-    const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
+    const uint32_t k = st.k, count = st.count;
+    const uint32_t kshift = 31 - k; // payload = (brev(win) >> 1) >> (31 - k), valid for k = 0 too
+    bool done = count == 0;
+    uint32_t limit = 128 * 32 - 96;  // refill when pos reaches within three words of the loaded range
     int32_t o0 = 0, o1 = 0, o2 = 0;
-    while (__ballot_sync(kFull, !done)) {
-        // refill: the block holding word (pos>>5)+3 must be resident
-        unsigned need = __ballot_sync(kFull, !done && ((((pos >> 5) + 3) >> 6) >= next_block));
+    const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
+    while (true) {
+        unsigned need = __ballot_sync(kFull, !done && pos >= limit);
         if (need) {
             __syncwarp();
-            while (need) {
+            do {
                 const int owner = __ffs(need) - 1;
                 need &= need - 1;
                 load_block(owner);
-            }
+            } while (need);
             __syncwarp();
+            limit = next_block * (64 * 32) - 96;
         }
+        // one parser step: either a whole symbol, or 32 more ones of a long unary run
+        const uint32_t ra = ((pos >> 5) & 127) * 32;
+        const uint32_t inv = ~__funnelshift_r(rb[ra], rb[ra + 32], pos);
+        const uint32_t ones = __clz(__brev(inv));      // 32 when the window is all ones
+        const uint32_t run = ones >> 5;                 // 1: no terminator in this window
+        const uint32_t p2 = pos + ones + 1 - run;
+        const uint32_t rc = ((p2 >> 5) & 127) * 32;
+        const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2);
+        const uint32_t payload = (__brev(win) >> 1) >> kshift;
+        const uint32_t q = q_acc + ones;
+        const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
+        const bool emit = !done && !run;
         if (!done) {
-            const uint32_t wi = pos >> 5;
-            const uint32_t a0 = ring[(wi & 127) * 32 + lane], a1 = ring[((wi + 1) & 127) * 32 + lane];
-            const uint32_t inv = ~__funnelshift_r(a0, a1, pos);
-            const bool run = inv == 0;                  // 32 more ones, no terminator yet
-            const uint32_t ones = run ? 32u : (uint32_t)(__ffs(inv) - 1);
-            const uint32_t q = q_acc + ones;
-            const uint32_t p2 = pos + ones + (run ? 0u : 1u);
-            const uint32_t wj = p2 >> 5;
-            const uint32_t b0 = ring[(wj & 127) * 32 + lane], b1 = ring[((wj + 1) & 127) * 32 + lane];
-            const uint32_t win = __funnelshift_r(b0, b1, p2);
-            const uint32_t payload = k ? (__brev(win) >> (32 - k)) : 0u;
-            if (run) {
-                q_acc = q;
-                pos = p2;
-            } else {
-                const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
-                q_acc = 0;
-                pos = p2 + k;
-                if (vec_out) {
-                    const uint32_t sel = i & 3u;
-                    if (sel == 0) o0 = v;
-                    else if (sel == 1) o1 = v;
-                    else if (sel == 2) o2 = v;
-                    else *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
-                } else {
-                    st.out[i] = v;
-                }
-                i++;
-                done = i == st.count;
-            }
+            q_acc = run ? q : 0;
+            pos = run ? p2 : p2 + k;
         }
+        const uint32_t sel = i & 3u;
+        if (vec_out) {
+            if (emit && sel == 3)
+                *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
+            o0 = sel == 0 ? v : o0;
+            o1 = sel == 1 ? v : o1;
+            o2 = sel == 2 ? v : o2;
+        } else if (emit) {
+            st.out[i] = v;
+        }
+        i += emit;
+        done = done || i == count;
+        if (!__any_sync(kFull, !done))
+            break;
     }
-    if (vec_out && st.count) {
-        const uint32_t rem = st.count & 3u, b = st.count - rem;
+    if (vec_out && count) {
+        const uint32_t rem = count & 3u, b = count - rem;
         if (rem > 0) st.out[b] = o0;
         if (rem > 1) st.out[b + 1] = o1;
         if (rem > 2) st.out[b + 2] = o2;

@@ -100,6 +100,16 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (cannot be taken
+    inside the bench: a number measured under a profiler is never a bench value)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return int(json.loads(p.read_text())[kernel]["traffic"])
+    except Exception:
+        return None
+
+
 def make_pcm(seed):
     from sela_b200 import synth
     return synth.sine_noise(SAMPLE_RATE, CHANNELS, seconds=SECONDS, seed=seed)
@@ -291,9 +301,10 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic("k_encode_units<stereo>"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": enc_bytes,
-                         "note": "issue/latency-bound FP64+INT64 work; see DESIGN.md roofline section"},
+                         "note": "FP64-latency / instruction-issue bound, not HBM bound (DESIGN.md 4); "
+                                 "traffic = dram read+write per launch from profiles/traffic.json (ncu)"},
         }
         if world == 1 and not args.no_cpu:
             info, (sf, d_ref, w_ref) = cpu_reference_leg(pcm_np)

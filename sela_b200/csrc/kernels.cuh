@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
         warp_rice_pack(cf.q, order, cq.k, cq.words, slot);
         warp_rice_pack(res, kFrame, cr.k, cr.words, slot + kSlotReflWords);
     }
+    // The residue row is dead now.  It only ever lived in L2 (written and re-read by this warp
+    // within microseconds); tell L2 to drop the dirty lines instead of writing 8 KB per unit back
+    // to HBM.
+    __syncwarp();
+    for (int l = lane; l < kFrame * 4 / 128; l += 32)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(res + l * 32) : "memory");
     if (lane == 0) {
         UnitRecord u;
         u.order = order;

@@ -90,17 +90,20 @@ __device__ __forceinline__ void unpack8(const uint4 v, int (&s)[8])
     s[6] = (int)(v.w << 16) >> 16; s[7] = (int)v.w >> 16;
 }
 
-// The signal one warp analyses: a channel of the frame held as int16 in shared
-// memory, or the difference ch0 - ch1 (src/frame/frame_encoder.cpp:20-24).
-// a/b point at sample 0 (16-byte aligned, kHistoryPad zeros in front).
+// The signal one warp analyses, held in ONE int16 row of shared memory: a channel of the
+// frame, or the 17-bit difference d = ch0 - ch1 (src/frame/frame_encoder.cpp:20-24) split as
+// d >> 1 in the row and d & 1 in a 2048-bit side array (so a difference unit needs no more
+// shared memory than a plain one and 24 units fit an SM).  `a` points at sample 0 (16-byte
+// aligned, kHistoryPad zeros in front); `lo` is nullptr for a plain channel, else bit j of
+// lo[] is d[j] & 1 (kHistoryPad zero bits in front as well).
 struct Signal {
     const int16_t *a;
-    const int16_t *b; // nullptr unless difference
+    const uint32_t *lo;
     __device__ __forceinline__ int at(int j) const
     {
         int v = a[j];
-        if (b)
-            v -= b[j];
+        if (lo)
+            v = (v << 1) | (int)((lo[j >> 5] >> (j & 31)) & 1u);
         return v;
     }
     // samples [8g, 8g+8) biased by 2^17 (g >= -kHistoryPad/8)
@@ -108,12 +111,11 @@ struct Signal {
     {
         int s[8];
         unpack8(*reinterpret_cast<const uint4 *>(a + 8 * g), s);
-        if (b) {
-            int t[8];
-            unpack8(*reinterpret_cast<const uint4 *>(b + 8 * g), t);
+        if (lo) {
+            const uint32_t bits = reinterpret_cast<const uint8_t *>(lo)[g];
 #pragma unroll
             for (int r = 0; r < 8; r++)
-                s[r] -= t[r];
+                s[r] = (s[r] << 1) | (int)((bits >> r) & 1u);
         }
 #pragma unroll
         for (int r = 0; r < 8; r++)

@@ -62,42 +62,63 @@ template <bool STEREO>
 __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
 {
     constexpr int kRow = kHistoryPad + kFrame;
-    constexpr int kChan = STEREO ? 2 : 1;
+    constexpr int kLoWords = (kHistoryPad + kFrame) / 32; // parity bits of a difference signal
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                    // [kChan][pad + 2048]
-    AnalysisScratch &scratch = *reinterpret_cast<AnalysisScratch *>(smem_raw + kChan * kRow * 2);
-    CoefSmem &cf = *reinterpret_cast<CoefSmem *>(smem_raw + kChan * kRow * 2 + sizeof(AnalysisScratch));
+    int16_t *s16 = reinterpret_cast<int16_t *>(smem_raw);                    // [pad + 2048]
+    uint32_t *lo_bits = reinterpret_cast<uint32_t *>(smem_raw + kRow * 2);    // [pad/32 + 64] (stereo only)
+    constexpr size_t kSigBytes = kRow * 2 + (STEREO ? kLoWords * 4 : 0);
+    AnalysisScratch &scratch = *reinterpret_cast<AnalysisScratch *>(smem_raw + kSigBytes);
+    CoefSmem &cf = *reinterpret_cast<CoefSmem *>(smem_raw + kSigBytes + sizeof(AnalysisScratch));
 
     const int lane = lane_id();
     const uint32_t unit = blockIdx.x;
     const uint32_t frame = STEREO ? unit / 3 : unit / p.channels;
     const uint32_t role = STEREO ? unit % 3 : unit % p.channels; // stereo: 0 ch0, 1 ch1, 2 ch0-ch1
 
-    // ---- stage the PCM (de-interleave to planar int16, zero history in front) ----
+    // ---- stage the signal (de-interleave to one planar int16 row, zero history in front) ----
     const int16_t *src = p.pcm + (size_t)frame * kFrame * p.channels;
-    for (int j = lane; j < kChan * kHistoryPad / 2; j += 32) {
-        const int c = j / (kHistoryPad / 2), o = j % (kHistoryPad / 2);
-        reinterpret_cast<uint32_t *>(s16 + c * kRow)[o] = 0;
-    }
-    int16_t *row0 = s16 + kHistoryPad;
+    for (int j = lane; j < kHistoryPad / 2; j += 32)
+        reinterpret_cast<uint32_t *>(s16)[j] = 0;
+    int16_t *row = s16 + kHistoryPad;
     Signal sig;
+    sig.a = row;
+    sig.lo = nullptr;
     if (STEREO) {
-        int16_t *row1 = row0 + kRow;
         const uint4 *src128 = reinterpret_cast<const uint4 *>(src); // 4 stereo sample pairs per load
-        for (int j = lane; j < kFrame / 4; j += 32) {
-            const uint4 v = src128[j];
-            const uint32_t l0 = __byte_perm(v.x, v.y, 0x5410), r0 = __byte_perm(v.x, v.y, 0x7632);
-            const uint32_t l1 = __byte_perm(v.z, v.w, 0x5410), r1 = __byte_perm(v.z, v.w, 0x7632);
-            reinterpret_cast<uint2 *>(row0)[j] = make_uint2(l0, l1);
-            reinterpret_cast<uint2 *>(row1)[j] = make_uint2(r0, r1);
+        if (role < 2) {
+            const uint32_t sel = role ? 0x7632 : 0x5410;
+            for (int j = lane; j < kFrame / 4; j += 32) {
+                const uint4 v = src128[j];
+                reinterpret_cast<uint2 *>(row)[j] = make_uint2(__byte_perm(v.x, v.y, sel), __byte_perm(v.z, v.w, sel));
+            }
+        } else {
+            // difference d = ch0 - ch1 (17 bits): d >> 1 into the row, d & 1 into the bit array
+            if (lane < kHistoryPad / 32)
+                lo_bits[lane] = 0;
+            uint32_t *lo = lo_bits + kHistoryPad / 32;
+            for (int it = 0; it < kFrame / 128; it++) {
+                const uint4 v = src128[it * 32 + lane];
+                const uint32_t pr[4] = {v.x, v.y, v.z, v.w};
+                int d[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    d[e] = ((int)(pr[e] << 16) >> 16) - ((int)pr[e] >> 16);
+                const uint32_t h01 = ((uint32_t)(d[0] >> 1) & 0xffffu) | ((uint32_t)(d[1] >> 1) << 16);
+                const uint32_t h23 = ((uint32_t)(d[2] >> 1) & 0xffffu) | ((uint32_t)(d[3] >> 1) << 16);
+                reinterpret_cast<uint2 *>(row)[it * 32 + lane] = make_uint2(h01, h23);
+                uint32_t nib = (d[0] & 1) | ((d[1] & 1) << 1) | ((d[2] & 1) << 2) | ((d[3] & 1) << 3);
+                nib <<= 4 * (lane & 7);
+                nib |= __shfl_xor_sync(kFull, nib, 1);
+                nib |= __shfl_xor_sync(kFull, nib, 2);
+                nib |= __shfl_xor_sync(kFull, nib, 4);
+                if ((lane & 7) == 0)
+                    lo[it * 4 + (lane >> 3)] = nib;
+            }
+            sig.lo = lo;
         }
-        sig.a = (role == 1) ? row1 : row0;
-        sig.b = (role == 2) ? row1 : nullptr;
     } else {
         for (int j = lane; j < kFrame; j += 32)
-            row0[j] = src[(size_t)j * p.channels + role];
-        sig.a = row0;
-        sig.b = nullptr;
+            row[j] = src[(size_t)j * p.channels + role];
     }
     __syncwarp();
 
@@ -140,7 +161,8 @@ __global__ void __launch_bounds__(32) k_encode_units(EncodeParams p)
 template <bool STEREO>
 constexpr size_t encode_smem_bytes()
 {
-    return (size_t)(STEREO ? 2 : 1) * (kHistoryPad + kFrame) * 2 + sizeof(AnalysisScratch) + sizeof(CoefSmem);
+    return (size_t)(kHistoryPad + kFrame) * 2 + (STEREO ? (kHistoryPad + kFrame) / 8 : 0) +
+           sizeof(AnalysisScratch) + sizeof(CoefSmem);
 }
 
 // Which unit is emitted for output subframe (frame, channel), and as what.

@@ -189,9 +189,9 @@ __device__ __noinline__ void warp_rice_pack(const int32_t *vals, int n, uint32_t
 // Words reach the parsers through a per-warp shared-memory ring: ring[w & 127][lane]
 // holds word w of lane's stream (bank = lane for every parser read).  The ring is
 // filled COOPERATIVELY, 64 words (two coalesced 128-byte loads by the whole warp) of
-// one stream at a time, whenever a lane is within three words of its loaded range --
-// so global memory only ever sees coalesced loads, and the parser's dependent chain is
-// LDS -> funnel shift -> ffs -> LDS -> funnel shift -> brev.
+// one stream at a time, ahead of need -- so global memory only ever sees coalesced
+// loads, and the parser's dependent chain is LDS -> funnel shift -> clz -> LDS ->
+// funnel shift -> brev.
 // Reads beyond n_words see zero bits (bounded, unlike the reference).
 struct RiceLaneStream {
     const uint32_t *src;
@@ -202,28 +202,62 @@ constexpr int kRiceRingWords = 128; // per lane
 constexpr int kRiceRingRows = kRiceRingWords + 1; // row 128 mirrors row 0, so word w+1 is always one row below word w
 
 // Returns (per lane) false if the stream needed more bits than n_words holds.
+//
+// Control structure: the parsers run kRiceBatch steps back to back with no warp votes and no
+// branches (the per-symbol recurrence pos -> LDS -> funnel shift -> clz -> pos is the whole
+// critical path); refills and the all-done test happen only at batch boundaries.  A refill is
+// two-phase: the coalesced loads for the next 64-word block of a lane are ISSUED at one
+// boundary and COMMITTED to the ring at the next, so their latency hides under a batch of
+// parsing.  Margins: a step consumes at most 2 words and looks 3 ahead, a batch 16 words.  A
+// lane WANTS its next block as soon as it enters the last loaded one (the block it left is then
+// free to overwrite); the request turns URGENT when another batch could run dry.  Each boundary
+// puts up to kRicePending requests in flight, urgent ones first; urgent requests that find no
+// slot are served synchronously, merely wanted ones wait for the next boundary.
+constexpr int kRiceBatch = 8;
+constexpr uint32_t kRiceWant = 64;   // ask for the next block on entering the last loaded one ...
+constexpr uint32_t kRiceUrgent = 35; // ... it becomes urgent when one more batch could run dry (3 + 16 + 16)
+constexpr int kRicePending = 8;      // blocks in flight per boundary; streams of equal bit rate ask in bursts
+
 __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
 {
     const int lane = lane_id();
     uint32_t next_block = 0; // per lane: next 64-word block of MY stream to load
-    auto load_block = [&](int owner) {
+
+    struct Fetch {
+        uint32_t v0, v1, w0; // this lane's two words of the block, and the word index of v0
+        int owner;           // uniform
+    };
+    auto issue = [&](int owner) -> Fetch {
+        Fetch f;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(
             shfl_u64(reinterpret_cast<unsigned long long>(st.src), owner));
         const uint32_t nw = __shfl_sync(kFull, st.n_words, owner);
         const uint32_t nb = __shfl_sync(kFull, next_block, owner);
-        const uint32_t w0 = nb * 64 + lane, w1 = w0 + 32;
-        const uint32_t v0 = w0 < nw ? __ldg(src + w0) : 0u;
-        const uint32_t v1 = w1 < nw ? __ldg(src + w1) : 0u;
-        ring[(w0 & 127) * 32 + owner] = v0; // column write: 32-way bank conflict, off the parsers' path
-        ring[(w1 & 127) * 32 + owner] = v1;
-        if ((w0 & 127) == 0)
-            ring[128 * 32 + owner] = v0;    // the mirror row
+        f.owner = owner;
+        f.w0 = nb * 64 + lane;
+        f.v0 = f.w0 < nw ? __ldg(src + f.w0) : 0u;
+        f.v1 = f.w0 + 32 < nw ? __ldg(src + f.w0 + 32) : 0u;
         if (lane == owner)
             next_block++;
+        return f;
     };
-    for (int owner = 0; owner < 32; owner++) {
-        load_block(owner);
-        load_block(owner);
+    auto commit = [&](const Fetch &f) {
+        ring[(f.w0 & 127) * 32 + f.owner] = f.v0; // column write: 32-way bank conflict, off the parsers' path
+        ring[((f.w0 + 32) & 127) * 32 + f.owner] = f.v1;
+        if ((f.w0 & 127) == 0)
+            ring[128 * 32 + f.owner] = f.v0;      // the mirror row
+    };
+    // initial fill: blocks 0 and 1 of every lane's stream, eight loads in flight at a time
+    for (int pass = 0; pass < 2; pass++) {
+        for (int base = 0; base < 32; base += 8) {
+            Fetch f[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                f[t] = issue(base + t);
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                commit(f[t]);
+        }
     }
     __syncwarp();
 
@@ -232,51 +266,76 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
     const uint32_t k = st.k, count = st.count;
     const uint32_t kshift = 31 - k; // payload = (brev(win) >> 1) >> (31 - k), valid for k = 0 too
     bool done = count == 0;
-    uint32_t limit = 128 * 32 - 96;  // refill when pos reaches within three words of the loaded range
     int32_t o0 = 0, o1 = 0, o2 = 0;
     const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
+    Fetch pend[kRicePending];
+    int n_pend = 0; // uniform
+
     while (true) {
-        unsigned need = __ballot_sync(kFull, !done && pos >= limit);
-        if (need) {
+        // ---- batch boundary ----
+        if (n_pend) {
             __syncwarp();
-            do {
-                const int owner = __ffs(need) - 1;
-                need &= need - 1;
-                load_block(owner);
-            } while (need);
+#pragma unroll
+            for (int t = 0; t < kRicePending; t++)
+                if (t < n_pend)
+                    commit(pend[t]);
+            n_pend = 0;
             __syncwarp();
-            limit = next_block * (64 * 32) - 96;
         }
-        // one parser step: either a whole symbol, or 32 more ones of a long unary run
-        const uint32_t ra = ((pos >> 5) & 127) * 32;
-        const uint32_t inv = ~__funnelshift_r(rb[ra], rb[ra + 32], pos);
-        const uint32_t ones = __clz(__brev(inv));      // 32 when the window is all ones
-        const uint32_t run = ones >> 5;                 // 1: no terminator in this window
-        const uint32_t p2 = pos + ones + 1 - run;
-        const uint32_t rc = ((p2 >> 5) & 127) * 32;
-        const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2);
-        const uint32_t payload = (__brev(win) >> 1) >> kshift;
-        const uint32_t q = q_acc + ones;
-        const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
-        const bool emit = !done && !run;
-        if (!done) {
-            q_acc = run ? q : 0;
-            pos = run ? p2 : p2 + k;
-        }
-        const uint32_t sel = i & 3u;
-        if (vec_out) {
-            if (emit && sel == 3)
-                *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
-            o0 = sel == 0 ? v : o0;
-            o1 = sel == 1 ? v : o1;
-            o2 = sel == 2 ? v : o2;
-        } else if (emit) {
-            st.out[i] = v;
-        }
-        i += emit;
-        done = done || i == count;
         if (!__any_sync(kFull, !done))
             break;
+        unsigned urgent = __ballot_sync(kFull, !done && (pos >> 5) + kRiceUrgent >= next_block * 64);
+        unsigned want = __ballot_sync(kFull, !done && (pos >> 5) + kRiceWant >= next_block * 64) & ~urgent;
+#pragma unroll
+        for (int t = 0; t < kRicePending; t++) {
+            unsigned &from = urgent ? urgent : want;
+            if (from) {
+                const int owner = __ffs(from) - 1;
+                from &= from - 1;
+                pend[t] = issue(owner);
+                n_pend = t + 1;
+            }
+        }
+        if (urgent) { // more urgent requests than slots (rare): serve them synchronously
+            __syncwarp();
+            do {
+                const int owner = __ffs(urgent) - 1;
+                urgent &= urgent - 1;
+                commit(issue(owner));
+            } while (urgent);
+            __syncwarp();
+        }
+        // ---- kRiceBatch parser steps: a whole symbol each, or 32 more ones of a long unary run ----
+#pragma unroll
+        for (int s = 0; s < kRiceBatch; s++) {
+            const uint32_t ra = ((pos >> 5) & 127) * 32;
+            const uint32_t inv = ~__funnelshift_r(rb[ra], rb[ra + 32], pos);
+            const uint32_t ones = __clz(__brev(inv));  // 32 when the window is all ones
+            const uint32_t run = ones >> 5;             // 1: no terminator in this window
+            const uint32_t p2 = pos + ones + 1 - run;
+            const uint32_t rc = ((p2 >> 5) & 127) * 32;
+            const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2);
+            const uint32_t payload = (__brev(win) >> 1) >> kshift;
+            const uint32_t q = q_acc + ones;
+            const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
+            const bool emit = !done && !run;
+            if (!done) {
+                q_acc = run ? q : 0;
+                pos = run ? p2 : p2 + k;
+            }
+            const uint32_t sel = i & 3u;
+            if (vec_out) {
+                if (emit && sel == 3)
+                    *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
+                o0 = sel == 0 ? v : o0;
+                o1 = sel == 1 ? v : o1;
+                o2 = sel == 2 ? v : o2;
+            } else if (emit) {
+                st.out[i] = v;
+            }
+            i += emit;
+            done = done || i == count;
+        }
     }
     if (vec_out && count) {
         const uint32_t rem = count & 3u, b = count - rem;

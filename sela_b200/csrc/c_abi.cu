@@ -157,7 +157,7 @@ int launch_check(const char *what)
 int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *d_descs,
                   uint32_t *d_words, size_t capacity, uint64_t *d_used, int32_t *d_status, void *d_ws,
                   size_t ws_bytes, cudaStream_t stream, bool fresh = true, cudaEvent_t before_scan = nullptr,
-                  cudaEvent_t after_scan = nullptr)
+                  cudaEvent_t after_scan = nullptr, unsigned long long *h_fill_after = nullptr)
 {
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
@@ -202,6 +202,10 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     k_encode_scan<<<1, 1024, 0, stream>>>(p);
     if (int rc = launch_check("k_encode_scan"))
         return rc;
+    // The fill level this chunk leaves behind must be captured BEFORE the next chunk's scan (on the
+    // other compute lane) may overwrite *d_used: copy it out now and only then release the event.
+    if (h_fill_after)
+        CUDA_TRY(cudaMemcpyAsync(h_fill_after, d_used, 8, cudaMemcpyDeviceToHost, stream));
     if (after_scan)
         CUDA_TRY(cudaEventRecord(after_scan, stream));
     k_encode_gather<<<(unsigned)((n_sub + 7) / 8), 256, 0, stream>>>(p);
@@ -463,10 +467,8 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
         CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
         if (int rc = encode_device(d_pcm + (size_t)f0 * channels * kFrame, nf, channels, d_descs + (size_t)f0 * channels,
                                    d_words, words_capacity, d_used, d_status, ws.ptr, ws.bytes, cs, false,
-                                   c ? g.ev_scan[c - 1] : nullptr, g.ev_scan[c]))
+                                   c ? g.ev_scan[c - 1] : nullptr, g.ev_scan[c], &g.h_totals[c + 1]))
             return rc;
-        // fill level after this chunk -> host (ordered after this chunk's scan; tiny)
-        CUDA_TRY(cudaMemcpyAsync(&g.h_totals[c + 1], d_used, 8, cudaMemcpyDeviceToHost, cs));
         CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
     }
     g.h_totals[0] = 0;

@@ -250,3 +250,87 @@ def test_large_batch_properties(O):
             n = int(sizes[2 * f + c])
             o1, o2 = int(a["refl_offset"]), int(b["refl_offset"])
             assert np.array_equal(w[o1:o1 + n], wr[o2:o2 + n]), (f, c)
+
+
+def test_pipelined_chunks_match_single_shot(O, monkeypatch):
+    """The host-buffer calls stream big batches in chunks (arena fill level chained through the
+    scan kernel).  Force many tiny chunks and compare with the oracle."""
+    pcm = _stereo_mix(23, 8)
+    d_ref, w_ref = O.encode_frames(pcm, 2)
+    for cf in ("1", "3", "7"):
+        monkeypatch.setenv("SELAB200_CHUNK_FRAMES", cf)
+        d, w = sela_b200.encode_frames(pcm, 2)
+        assert d.tobytes() == d_ref.tobytes() and np.array_equal(w, w_ref), cf
+        assert np.array_equal(sela_b200.decode_frames(d, w, 2), pcm.reshape(-1)), cf
+    monkeypatch.delenv("SELAB200_CHUNK_FRAMES")
+
+
+def test_decode_descriptors_in_arbitrary_arena_order(O):
+    """Descriptors need not reference the arena in file order: permute the per-subframe word
+    blocks and decode through the chunked path."""
+    pcm = synth.sine_noise(44100, 2, n_frames=12, seed=6)
+    d, w = O.encode_frames(pcm, 2)
+    rng = np.random.default_rng(0)
+    order = rng.permutation(d.size)
+    d2 = d.copy()
+    parts, cursor = [], 0
+    for idx in order:
+        a, n1, b, n2 = int(d["refl_offset"][idx]), int(d["refl_words"][idx]), int(d["res_offset"][idx]), int(d["res_words"][idx])
+        parts.append(w[b:b + n2]); d2["res_offset"][idx] = cursor; cursor += n2      # residues first, for a change
+        parts.append(w[a:a + n1]); d2["refl_offset"][idx] = cursor; cursor += n1
+    w2 = np.concatenate(parts)
+    import os
+    os.environ["SELAB200_CHUNK_FRAMES"] = "4"
+    try:
+        assert np.array_equal(sela_b200.decode_frames(d2, w2, 2), pcm.reshape(-1))
+    finally:
+        del os.environ["SELAB200_CHUNK_FRAMES"]
+
+
+def test_difference_coding_outside_stereo_uses_general_kernel(O):
+    """The reference DEcoder accepts difference-coded subframes at any channel count
+    (src/frame/frame_decoder.cpp:40-69) although its encoder only emits them for stereo.  Build a
+    3-channel frame whose channel 2 is coded as channel0 - channel2 and check against the oracle."""
+    pcm = synth.sine_noise(32000, 3, n_frames=3, seed=12).astype(np.int32)
+    pcm[:, 2] = pcm[:, 0] - (pcm[:, 2] >> 4)
+    pcm = np.clip(pcm, -32768, 32767).astype(np.int16)
+    d, w = O.encode_frames(pcm, 3)
+    descs, parts, cursor = d.copy(), [], 0
+    for f in range(3):
+        frame = pcm[f * FRAME:(f + 1) * FRAME].astype(np.int32)
+        for c in range(3):
+            i = 3 * f + c
+            if c == 2:
+                a = O.lpc_analyse(frame[:, 0] - frame[:, 2])
+                kq, wq = O.rice_encode(a["q"]); kr, wr = O.rice_encode(a["res"])
+                descs[i]["subframe_type"], descs[i]["parent_channel"] = 1, 0
+                descs[i]["refl_rice_param"], descs[i]["refl_words"], descs[i]["lpc_order"] = kq, wq.size, a["order"]
+                descs[i]["res_rice_param"], descs[i]["res_words"] = kr, wr.size
+            else:
+                wq = w[int(d[i]["refl_offset"]):int(d[i]["refl_offset"]) + int(d[i]["refl_words"])]
+                wr = w[int(d[i]["res_offset"]):int(d[i]["res_offset"]) + int(d[i]["res_words"])]
+            descs[i]["refl_offset"] = cursor; parts.append(wq); cursor += wq.size
+            descs[i]["res_offset"] = cursor; parts.append(wr); cursor += wr.size
+    words = np.concatenate(parts)
+    want = O.decode_frames(descs, words, 3)
+    assert np.array_equal(want, pcm.reshape(-1))
+    assert np.array_equal(sela_b200.decode_frames(descs, words, 3), want)
+
+
+def test_rice_streams_with_long_unary_runs_and_k_extremes(O):
+    rng = np.random.default_rng(77)
+    cases = [np.full(64, 1 << 19, np.int32), np.full(2048, -1, np.int32),
+             (rng.integers(0, 2, 2048) * (1 << 18)).astype(np.int32),
+             rng.integers(-(1 << 23), 1 << 23, 2048).astype(np.int32)]
+    vals = np.zeros((len(cases), 2048), np.int32)
+    counts = np.array([c.size for c in cases], np.uint32)
+    for i, c in enumerate(cases):
+        vals[i, :c.size] = c
+    k, nw, words = sela_b200.rice_encode(vals, counts, words_stride=40000)
+    for i, c in enumerate(cases):
+        ko, wo = O.rice_encode(c)
+        assert (k[i], nw[i]) == (ko, wo.size), i
+        assert np.array_equal(words[i, :nw[i]], wo), i
+    out = sela_b200.rice_decode(words, nw, k, counts, out_stride=2048)
+    for i, c in enumerate(cases):
+        assert np.array_equal(out[i, :c.size], c), i

@@ -64,16 +64,17 @@ struct DeviceBuffer {
 };
 
 constexpr int kMaxChunks = 64;
+constexpr int kLanes = 8; // concurrent compute streams of the pipelined host calls
 
 struct Context {
     bool ready = false;
     int device = -1;
     cudaStream_t stream = nullptr;                 // stage-level calls
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined batch calls: copy engines ...
-    cudaStream_t s_compute[2] = {nullptr, nullptr}; // ... and two alternating compute lanes
+    cudaStream_t s_compute[kLanes] = {};           // ... and alternating compute lanes
     cudaEvent_t ev_h2d[kMaxChunks], ev_done[kMaxChunks], ev_scan[kMaxChunks], ev_reset;
     bool events = false;
-    DeviceBuffer in, descs, words, work, work2, aux, small;
+    DeviceBuffer in, descs, words, work, lane_work[kLanes], aux, small;
     int32_t *h_small = nullptr;                    // pinned: [0] status, [2..3] words_used
     unsigned long long *h_totals = nullptr;        // pinned: arena fill level after each chunk
 } g;
@@ -83,9 +84,13 @@ struct Context {
 struct PipelineDrain {
     ~PipelineDrain()
     {
-        for (cudaStream_t st : {g.s_h2d, g.s_compute[0], g.s_compute[1], g.s_d2h})
-            if (st)
-                cudaStreamSynchronize(st);
+        if (g.s_h2d)
+            cudaStreamSynchronize(g.s_h2d);
+        for (int i = 0; i < kLanes; i++)
+            if (g.s_compute[i])
+                cudaStreamSynchronize(g.s_compute[i]);
+        if (g.s_d2h)
+            cudaStreamSynchronize(g.s_d2h);
     }
 };
 
@@ -294,8 +299,8 @@ int selab200_init(int device)
         CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[0], cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[1], cudaStreamNonBlocking));
+        for (int i = 0; i < kLanes; i++)
+            CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[i], cudaStreamNonBlocking));
     }
     if (!g.events) {
         for (int i = 0; i < kMaxChunks; i++) {
@@ -327,7 +332,8 @@ void selab200_shutdown(void)
     g.descs.release();
     g.words.release();
     g.work.release();
-    g.work2.release();
+    for (int i = 0; i < kLanes; i++)
+        g.lane_work[i].release();
     g.aux.release();
     g.small.release();
     if (g.h_small)
@@ -336,10 +342,15 @@ void selab200_shutdown(void)
     if (g.h_totals)
         cudaFreeHost(g.h_totals);
     g.h_totals = nullptr;
-    for (cudaStream_t st : {g.stream, g.s_h2d, g.s_d2h, g.s_compute[0], g.s_compute[1]})
+    for (cudaStream_t st : {g.stream, g.s_h2d, g.s_d2h})
         if (st)
             cudaStreamDestroy(st);
-    g.stream = g.s_h2d = g.s_d2h = g.s_compute[0] = g.s_compute[1] = nullptr;
+    for (int i = 0; i < kLanes; i++) {
+        if (g.s_compute[i])
+            cudaStreamDestroy(g.s_compute[i]);
+        g.s_compute[i] = nullptr;
+    }
+    g.stream = g.s_h2d = g.s_d2h = nullptr;
     if (g.events)
         for (int i = 0; i < kMaxChunks; i++) {
             cudaEventDestroy(g.ev_h2d[i]);
@@ -446,8 +457,9 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(words_capacity * 4 + 16)) return rc;
-    if (int rc = g.work.ensure(ws_bytes)) return rc;
-    if (int rc = g.work2.ensure(n_chunks > 1 ? ws_bytes : 0)) return rc;
+    constexpr int kEncLanes = 2;
+    for (int i = 0; i < kEncLanes && (uint32_t)i < n_chunks; i++)
+        if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
     int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
     uint64_t *d_used = reinterpret_cast<uint64_t *>(static_cast<char *>(g.small.ptr) + 8);
     int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
@@ -456,14 +468,15 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
 
     CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
     CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
-    CUDA_TRY(cudaStreamWaitEvent(g.s_compute[1], g.ev_reset, 0));
+    for (int i = 1; i < kLanes; i++)
+        CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
         CUDA_TRY(cudaMemcpyAsync(d_pcm + (size_t)f0 * channels * kFrame, pcm + (size_t)f0 * channels * kFrame,
                                  nf * frame_bytes, cudaMemcpyHostToDevice, g.s_h2d));
         CUDA_TRY(cudaEventRecord(g.ev_h2d[c], g.s_h2d));
-        cudaStream_t cs = g.s_compute[c & 1];
-        DeviceBuffer &ws = (c & 1) ? g.work2 : g.work;
+        cudaStream_t cs = g.s_compute[c % kEncLanes];
+        DeviceBuffer &ws = g.lane_work[c % kEncLanes];
         CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
         if (int rc = encode_device(d_pcm + (size_t)f0 * channels * kFrame, nf, channels, d_descs + (size_t)f0 * channels,
                                    d_words, words_capacity, d_used, d_status, ws.ptr, ws.bytes, cs, false,
@@ -483,8 +496,8 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
                                  g.s_d2h));
         CUDA_TRY(cudaMemcpyAsync(words + lo, d_words + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, g.s_d2h));
     }
-    CUDA_TRY(cudaStreamSynchronize(g.s_compute[0]));
-    CUDA_TRY(cudaStreamSynchronize(g.s_compute[1]));
+    for (int i = 0; i < kEncLanes; i++)
+        CUDA_TRY(cudaStreamSynchronize(g.s_compute[i]));
     CUDA_TRY(cudaMemcpyAsync(g.h_small, g.small.ptr, 16, cudaMemcpyDeviceToHost, g.s_d2h));
     CUDA_TRY(cudaStreamSynchronize(g.s_d2h));
     uint64_t used;
@@ -508,7 +521,10 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
     if (n_frames == 0)
         return 0;
     PipelineDrain drain;
-    const uint32_t cf = chunk_frames_for(n_frames, 4);
+    // Every chunk gets its own compute lane (up to kLanes): the Rice kernel is one lane per stream
+    // and latency-bound (about 0.4 ms however small the chunk), so the chunks' Rice kernels must
+    // overlap each other and the synthesis kernels of earlier chunks rather than queue up.
+    const uint32_t cf = chunk_frames_for(n_frames, 8);
     const uint32_t n_chunks = (n_frames + cf - 1) / cf;
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
@@ -516,8 +532,8 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(n_words * 4 + 16)) return rc;
-    if (int rc = g.work.ensure(ws_bytes)) return rc;
-    if (int rc = g.work2.ensure(n_chunks > 1 ? ws_bytes : 0)) return rc;
+    for (int i = 0; i < kLanes && (uint32_t)i < n_chunks; i++)
+        if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
     int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
     int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
     selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
@@ -525,7 +541,8 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
 
     CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
     CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
-    CUDA_TRY(cudaStreamWaitEvent(g.s_compute[1], g.ev_reset, 0));
+    for (int i = 1; i < kLanes; i++)
+        CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
         // the words this chunk's descriptors reference (descriptors need not be in arena order)
@@ -546,8 +563,8 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
         if (hi > lo)
             CUDA_TRY(cudaMemcpyAsync(d_words + lo, words + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, g.s_h2d));
         CUDA_TRY(cudaEventRecord(g.ev_h2d[c], g.s_h2d));
-        cudaStream_t cs = g.s_compute[c & 1];
-        DeviceBuffer &ws = (c & 1) ? g.work2 : g.work;
+        cudaStream_t cs = g.s_compute[c % kLanes];
+        DeviceBuffer &ws = g.lane_work[c % kLanes];
         CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
         if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_words, n_words,
                                    d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))

@@ -286,14 +286,16 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
             break;
         unsigned urgent = __ballot_sync(kFull, !done && (pos >> 5) + kRiceUrgent >= next_block * 64);
         unsigned want = __ballot_sync(kFull, !done && (pos >> 5) + kRiceWant >= next_block * 64) & ~urgent;
+        if (urgent | want) { // most boundaries have nothing to fetch
 #pragma unroll
-        for (int t = 0; t < kRicePending; t++) {
-            unsigned &from = urgent ? urgent : want;
-            if (from) {
-                const int owner = __ffs(from) - 1;
-                from &= from - 1;
-                pend[t] = issue(owner);
-                n_pend = t + 1;
+            for (int t = 0; t < kRicePending; t++) {
+                unsigned &from = urgent ? urgent : want;
+                if (from) {
+                    const int owner = __ffs(from) - 1;
+                    from &= from - 1;
+                    pend[t] = issue(owner);
+                    n_pend = t + 1;
+                }
             }
         }
         if (urgent) { // more urgent requests than slots (rare): serve them synchronously

@@ -133,6 +133,14 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
                                   int16_t *d_pcm_out, int32_t *d_status, void *d_workspace,
                                   size_t workspace_bytes, void *stream);
 
+/* The Rice-decode kernel (K5 of SURVEY.md 2) on its own, device resident: the residue streams of
+ * every subframe -> d_residues[subframe][2048] int32, i.e. rice::RiceDecoder::process
+ * (src/rice/rice_decoder.cpp:54-61) over a batch.  Algorithmic bytes: the words read + 4 B per
+ * sample written.  Asynchronous on `stream`. */
+int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_t n_frames,
+                                       uint32_t channels, const uint32_t *d_words, size_t n_words,
+                                       int32_t *d_residues, int32_t *d_status, void *stream);
+
 /* ------------------------------------------ stage level (host buffers) -- */
 
 /* lpc::ResidueGenerator::process (src/lpc/residue_generator.cpp:121-134) for

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "selab200_encode_frames_device": (_I, [_V, _U32, _U32, _V, _V, _SZ, _V, _V, _V, _SZ, _V]),
     "selab200_decode_workspace_bytes": (_SZ, [_U32, _U32]),
     "selab200_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V, _SZ, _V]),
+    "selab200_rice_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V]),
     "selab200_lpc_residues": (_I, [_V, _U32, _V, _V, _V]),
     "selab200_lpc_samples": (_I, [_V, _U32, _V, _V, _V]),
     "selab200_rice_encode": (_I, [_V, _V, _U32, _U32, _V, _V, _V, _U32]),

@@ -217,6 +217,28 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     return launch_check("k_encode_gather");
 }
 
+// K5 launch.  Small batches are starved for parallelism (one lane per stream): the big ring with
+// long vote-free batches is fastest.  From a few hundred thousand streams on the SMs fill up and the
+// half-size ring, which doubles the resident warps, wins (tools/rice_decode_roofline.py).
+int rice_ring_override()
+{
+    const char *env = std::getenv("SELAB200_RICE_RING"); // 64 / 128: tuning and tests only
+    return env ? std::atoi(env) : 0;
+}
+
+int launch_rice_decode(const DecodeParams &p, int which, cudaStream_t stream)
+{
+    const size_t n_sub = (size_t)p.n_frames * p.channels;
+    const unsigned blocks = (unsigned)((n_sub + 32 * kRiceWarps - 1) / (32 * kRiceWarps));
+    const int forced = rice_ring_override();
+    const bool small_ring = forced ? forced == 64 : n_sub >= 65536;
+    if (small_ring)
+        k_rice_decode<64, 4><<<blocks, 32 * kRiceWarps, 0, stream>>>(p, which);
+    else
+        k_rice_decode<128, 8><<<blocks, 32 * kRiceWarps, 0, stream>>>(p, which);
+    return launch_check(which ? "k_rice_decode(res)" : "k_rice_decode(refl)");
+}
+
 int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
                   const uint32_t *d_words, size_t n_words, int16_t *d_pcm, int32_t *d_status, void *d_ws,
                   size_t ws_bytes, cudaStream_t stream, bool fresh = true)
@@ -240,12 +262,9 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     p.status = d_status;
     p.ws_q = static_cast<int32_t *>(d_ws);
     p.ws_res = reinterpret_cast<int32_t *>(static_cast<char *>(d_ws) + align256(n_sub * 128 * 4));
-    const unsigned blocks = (unsigned)((n_sub + 32 * kRiceWarps - 1) / (32 * kRiceWarps));
-    k_rice_decode<<<blocks, 32 * kRiceWarps, 0, stream>>>(p, 0);
-    if (int rc = launch_check("k_rice_decode(refl)"))
+    if (int rc = launch_rice_decode(p, 0, stream))
         return rc;
-    k_rice_decode<<<blocks, 32 * kRiceWarps, 0, stream>>>(p, 1);
-    if (int rc = launch_check("k_rice_decode(res)"))
+    if (int rc = launch_rice_decode(p, 1, stream))
         return rc;
     p.fallback_only = 1;
     k_synthesise_quad<<<(unsigned)((n_sub + 3) / 4), 32, 0, stream>>>(p);
@@ -434,6 +453,34 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
 //   s_d2h      results of chunk c-1 come down
 // With pinned host buffers (selab200_host_alloc) the three overlap; pageable memory works
 // but serialises inside the driver.
+int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
+                                       const uint32_t *d_words, size_t n_words, int32_t *d_residues,
+                                       int32_t *d_status, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!d_descs || !d_words || !d_residues || !d_status)
+        return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (n_frames == 0)
+        return 0;
+    DecodeParams p;
+    p.descs = d_descs;
+    p.n_frames = n_frames;
+    p.channels = channels;
+    p.words = d_words;
+    p.n_words = n_words;
+    p.pcm_out = nullptr;
+    p.status = d_status;
+    p.ws_q = nullptr;
+    p.ws_res = d_residues;
+    p.fallback_only = 0;
+    return launch_rice_decode(p, 1, (cudaStream_t)stream);
+}
+
 int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
                            selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
                            size_t *words_used)

@@ -315,11 +315,13 @@ struct DecodeParams {
     int fallback_only;
 };
 
-// K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams, 1: residue streams.
+// K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams (-> ws_q), 1: residue
+// streams (-> ws_res).
 constexpr int kRiceWarps = 2;
+template <int RING, int BATCH>
 __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p, int which)
 {
-    __shared__ uint32_t ring[kRiceWarps][kRiceRingRows * 32];
+    __shared__ uint32_t ring[kRiceWarps][(RING + 1) * 32];
     const uint32_t sub = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_sub = p.n_frames * p.channels;
     RiceLaneStream st;
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p,
             st.out = p.ws_res + (size_t)sub * kFrame;
         }
     }
-    if (!warp_rice_decode32(ring[warp_id()], st))
+    if (!warp_rice_decode32<RING, BATCH>(ring[warp_id()], st))
         raise_status(p.status, SELAB200_ERR_BITSTREAM);
 }
 
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
     const uint32_t *words, const uint32_t *n_words, uint32_t words_stride, const uint32_t *k,
     const uint32_t *counts, uint32_t n_streams, int32_t *out, uint32_t out_stride, int32_t *status)
 {
-    __shared__ uint32_t ring[kRiceWarps][kRiceRingRows * 32];
+    __shared__ uint32_t ring[kRiceWarps][(128 + 1) * 32];
     const uint32_t st_i = blockIdx.x * blockDim.x + threadIdx.x;
     RiceLaneStream st;
     st.src = words;
@@ -666,7 +668,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
             st.out = out + (size_t)st_i * out_stride;
         }
     }
-    warp_rice_decode32(ring[warp_id()], st);
+    warp_rice_decode32<128, 8>(ring[warp_id()], st);
 }
 
 } // namespace selab200

@@ -198,34 +198,40 @@ struct RiceLaneStream {
     uint32_t n_words, k, count;
     int32_t *out;
 };
-constexpr int kRiceRingWords = 128; // per lane
-constexpr int kRiceRingRows = kRiceRingWords + 1; // row 128 mirrors row 0, so word w+1 is always one row below word w
-
-// Returns (per lane) false if the stream needed more bits than n_words holds.
+// Ring geometry is a template parameter: RING words per lane (two blocks of RING/2), BATCH parser
+// steps between boundaries.  <128, 8> (16.5 KB per warp) is the default; <64, 4> (8.3 KB) doubles
+// the resident warps and is what very large batches use, where the kernel stops being starved for
+// parallelism and becomes issue-bound.
 //
-// Control structure: the parsers run kRiceBatch steps back to back with no warp votes and no
+// Control structure: the parsers run BATCH steps back to back with no warp votes and no
 // branches (the per-symbol recurrence pos -> LDS -> funnel shift -> clz -> pos is the whole
 // critical path); refills and the all-done test happen only at batch boundaries.  A refill is
-// two-phase: the coalesced loads for the next 64-word block of a lane are ISSUED at one
-// boundary and COMMITTED to the ring at the next, so their latency hides under a batch of
-// parsing.  Margins: a step consumes at most 2 words and looks 3 ahead, a batch 16 words.  A
-// lane WANTS its next block as soon as it enters the last loaded one (the block it left is then
-// free to overwrite); the request turns URGENT when another batch could run dry.  Each boundary
-// puts up to kRicePending requests in flight, urgent ones first; urgent requests that find no
-// slot are served synchronously, merely wanted ones wait for the next boundary.
-constexpr int kRiceBatch = 8;
-constexpr uint32_t kRiceWant = 64;   // ask for the next block on entering the last loaded one ...
-constexpr uint32_t kRiceUrgent = 35; // ... it becomes urgent when one more batch could run dry (3 + 16 + 16)
-constexpr int kRicePending = 8;      // blocks in flight per boundary; streams of equal bit rate ask in bursts
+// two-phase: the coalesced loads for the next block of a lane are ISSUED at one boundary and
+// COMMITTED to the ring at the next, so their latency hides under a batch of parsing.  Margins: a
+// step consumes at most 2 words and looks 3 ahead, a batch 2*BATCH words.  A lane WANTS its next
+// block as soon as it enters the last loaded one (the block it left is then free to overwrite);
+// the request turns URGENT when another batch could run dry.  Each boundary puts up to
+// kRicePending requests in flight, urgent ones first; urgent requests that find no slot are
+// served synchronously, merely wanted ones wait for the next boundary.
+constexpr int kRicePending = 8; // blocks in flight per boundary; streams of equal bit rate ask in bursts
 
+// rows of a ring: RING + 1, the last row mirrors row 0 so that word w+1 is always one row below word w
+
+// Returns (per lane) false if the stream needed more bits than n_words holds.
+template <int RING, int BATCH>
 __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
 {
+    constexpr uint32_t kBlock = RING / 2;               // words per refill
+    constexpr uint32_t kPerLane = kBlock / 32;          // words each lane loads per refill (1 or 2)
+    constexpr uint32_t kWant = kBlock;
+    constexpr uint32_t kUrgent = 3 + 4 * BATCH;         // lookahead + the batch in flight + the one before
+    static_assert(kUrgent < kBlock && (RING == 64 || RING == 128), "ring too small for the batch");
     const int lane = lane_id();
-    uint32_t next_block = 0; // per lane: next 64-word block of MY stream to load
+    uint32_t next_block = 0; // per lane: next block of MY stream to load
 
     struct Fetch {
-        uint32_t v0, v1, w0; // this lane's two words of the block, and the word index of v0
-        int owner;           // uniform
+        uint32_t v[kPerLane], w0; // this lane's words of the block, and the word index of v[0]
+        int owner;                // uniform
     };
     auto issue = [&](int owner) -> Fetch {
         Fetch f;
@@ -234,18 +240,20 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
         const uint32_t nw = __shfl_sync(kFull, st.n_words, owner);
         const uint32_t nb = __shfl_sync(kFull, next_block, owner);
         f.owner = owner;
-        f.w0 = nb * 64 + lane;
-        f.v0 = f.w0 < nw ? __ldg(src + f.w0) : 0u;
-        f.v1 = f.w0 + 32 < nw ? __ldg(src + f.w0 + 32) : 0u;
+        f.w0 = nb * kBlock + lane;
+#pragma unroll
+        for (uint32_t e = 0; e < kPerLane; e++)
+            f.v[e] = f.w0 + 32 * e < nw ? __ldg(src + f.w0 + 32 * e) : 0u;
         if (lane == owner)
             next_block++;
         return f;
     };
     auto commit = [&](const Fetch &f) {
-        ring[(f.w0 & 127) * 32 + f.owner] = f.v0; // column write: 32-way bank conflict, off the parsers' path
-        ring[((f.w0 + 32) & 127) * 32 + f.owner] = f.v1;
-        if ((f.w0 & 127) == 0)
-            ring[128 * 32 + f.owner] = f.v0;      // the mirror row
+#pragma unroll
+        for (uint32_t e = 0; e < kPerLane; e++) // column writes: 32-way bank conflict, off the parsers' path
+            ring[((f.w0 + 32 * e) & (RING - 1)) * 32 + f.owner] = f.v[e];
+        if ((f.w0 & (RING - 1)) == 0)
+            ring[RING * 32 + f.owner] = f.v[0]; // the mirror row
     };
     // initial fill: blocks 0 and 1 of every lane's stream, eight loads in flight at a time
     for (int pass = 0; pass < 2; pass++) {
@@ -284,8 +292,8 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
         }
         if (!__any_sync(kFull, !done))
             break;
-        unsigned urgent = __ballot_sync(kFull, !done && (pos >> 5) + kRiceUrgent >= next_block * 64);
-        unsigned want = __ballot_sync(kFull, !done && (pos >> 5) + kRiceWant >= next_block * 64) & ~urgent;
+        unsigned urgent = __ballot_sync(kFull, !done && (pos >> 5) + kUrgent >= next_block * kBlock);
+        unsigned want = __ballot_sync(kFull, !done && (pos >> 5) + kWant >= next_block * kBlock) & ~urgent;
         if (urgent | want) { // most boundaries have nothing to fetch
 #pragma unroll
             for (int t = 0; t < kRicePending; t++) {
@@ -307,15 +315,15 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
             } while (urgent);
             __syncwarp();
         }
-        // ---- kRiceBatch parser steps: a whole symbol each, or 32 more ones of a long unary run ----
+        // ---- BATCH parser steps: a whole symbol each, or 32 more ones of a long unary run ----
 #pragma unroll
-        for (int s = 0; s < kRiceBatch; s++) {
-            const uint32_t ra = ((pos >> 5) & 127) * 32;
+        for (int s = 0; s < BATCH; s++) {
+            const uint32_t ra = ((pos >> 5) & (RING - 1)) * 32;
             const uint32_t inv = ~__funnelshift_r(rb[ra], rb[ra + 32], pos);
             const uint32_t ones = __clz(__brev(inv));  // 32 when the window is all ones
             const uint32_t run = ones >> 5;             // 1: no terminator in this window
             const uint32_t p2 = pos + ones + 1 - run;
-            const uint32_t rc = ((p2 >> 5) & 127) * 32;
+            const uint32_t rc = ((p2 >> 5) & (RING - 1)) * 32;
             const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2);
             const uint32_t payload = (__brev(win) >> 1) >> kshift;
             const uint32_t q = q_acc + ones;

@@ -217,25 +217,12 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     return launch_check("k_encode_gather");
 }
 
-// K5 launch.  Small batches are starved for parallelism (one lane per stream): the big ring with
-// long vote-free batches is fastest.  From a few hundred thousand streams on the SMs fill up and the
-// half-size ring, which doubles the resident warps, wins (tools/rice_decode_roofline.py).
-int rice_ring_override()
-{
-    const char *env = std::getenv("SELAB200_RICE_RING"); // 64 / 128: tuning and tests only
-    return env ? std::atoi(env) : 0;
-}
-
+// K5 launch: 64-word rings (8.3 KB per warp), eight parser steps per batch.
 int launch_rice_decode(const DecodeParams &p, int which, cudaStream_t stream)
 {
     const size_t n_sub = (size_t)p.n_frames * p.channels;
     const unsigned blocks = (unsigned)((n_sub + 32 * kRiceWarps - 1) / (32 * kRiceWarps));
-    const int forced = rice_ring_override();
-    const bool small_ring = forced ? forced == 64 : n_sub >= 65536;
-    if (small_ring)
-        k_rice_decode<64, 4><<<blocks, 32 * kRiceWarps, 0, stream>>>(p, which);
-    else
-        k_rice_decode<128, 8><<<blocks, 32 * kRiceWarps, 0, stream>>>(p, which);
+    k_rice_decode<kRiceRing, kRiceBatch><<<blocks, 32 * kRiceWarps, 0, stream>>>(p, which);
     return launch_check(which ? "k_rice_decode(res)" : "k_rice_decode(refl)");
 }
 

@@ -318,6 +318,7 @@ struct DecodeParams {
 // K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams (-> ws_q), 1: residue
 // streams (-> ws_res).
 constexpr int kRiceWarps = 2;
+constexpr int kRiceRing = 64, kRiceBatch = 8;
 template <int RING, int BATCH>
 __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p, int which)
 {
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
     const uint32_t *words, const uint32_t *n_words, uint32_t words_stride, const uint32_t *k,
     const uint32_t *counts, uint32_t n_streams, int32_t *out, uint32_t out_stride, int32_t *status)
 {
-    __shared__ uint32_t ring[kRiceWarps][(128 + 1) * 32];
+    __shared__ uint32_t ring[kRiceWarps][(kRiceRing + 1) * 32];
     const uint32_t st_i = blockIdx.x * blockDim.x + threadIdx.x;
     RiceLaneStream st;
     st.src = words;
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode_streams(
             st.out = out + (size_t)st_i * out_stride;
         }
     }
-    warp_rice_decode32<128, 8>(ring[warp_id()], st);
+    warp_rice_decode32<kRiceRing, kRiceBatch>(ring[warp_id()], st);
 }
 
 } // namespace selab200

@@ -186,134 +186,100 @@ __device__ __noinline__ void warp_rice_pack(const int32_t *vals, int n, uint32_t
 // is inherently sequential, so the parallelism is across streams (subframes); the 32
 // lanes of a warp run the same branch-free scalar parser on 32 different streams.
 //
-// Words reach the parsers through a per-warp shared-memory ring: ring[w & 127][lane]
-// holds word w of lane's stream (bank = lane for every parser read).  The ring is
-// filled COOPERATIVELY, 64 words (two coalesced 128-byte loads by the whole warp) of
-// one stream at a time, ahead of need -- so global memory only ever sees coalesced
-// loads, and the parser's dependent chain is LDS -> funnel shift -> clz -> LDS ->
-// funnel shift -> brev.
-// Reads beyond n_words see zero bits (bounded, unlike the reference).
+// Words reach the parser through a per-warp shared-memory ring, ring[w & (RING-1)][lane]
+// (bank = lane for every access, so neither the parser's reads nor the refill's writes
+// ever conflict).  Each lane keeps its own ring topped up with 16-byte loads from its own
+// stream (aligned down; the words in front of the stream are skipped, words past its end
+// read as zero -- bounded, unlike the reference), issued one batch ahead of use.
+// The parser's dependent chain per symbol is
+//     pos -> LDS pair -> funnel shift -> clz -> pos'   (+ LDS pair -> funnel shift -> brev for the payload)
+// and BATCH such steps run back to back with no votes and no branches; refills and the
+// all-done test happen at batch boundaries only.
+// Margins: a step consumes at most 2 words and looks 3 ahead, a batch 2*BATCH words; loads
+// issued at one boundary are committed at the next, so a lane needs 3 + 4*BATCH committed
+// words ahead of it at every boundary -- the top-up keeps about RING, and a lane that
+// still falls short (only streams running near 2 words per symbol can) refills on the spot.
 struct RiceLaneStream {
     const uint32_t *src;
     uint32_t n_words, k, count;
     int32_t *out;
 };
-// Ring geometry is a template parameter: RING words per lane (two blocks of RING/2), BATCH parser
-// steps between boundaries.  <128, 8> (16.5 KB per warp) is the default; <64, 4> (8.3 KB) doubles
-// the resident warps and is what very large batches use, where the kernel stops being starved for
-// parallelism and becomes issue-bound.
-//
-// Control structure: the parsers run BATCH steps back to back with no warp votes and no
-// branches (the per-symbol recurrence pos -> LDS -> funnel shift -> clz -> pos is the whole
-// critical path); refills and the all-done test happen only at batch boundaries.  A refill is
-// two-phase: the coalesced loads for the next block of a lane are ISSUED at one boundary and
-// COMMITTED to the ring at the next, so their latency hides under a batch of parsing.  Margins: a
-// step consumes at most 2 words and looks 3 ahead, a batch 2*BATCH words.  A lane WANTS its next
-// block as soon as it enters the last loaded one (the block it left is then free to overwrite);
-// the request turns URGENT when another batch could run dry.  Each boundary puts up to
-// kRicePending requests in flight, urgent ones first; urgent requests that find no slot are
-// served synchronously, merely wanted ones wait for the next boundary.
-constexpr int kRicePending = 8; // blocks in flight per boundary; streams of equal bit rate ask in bursts
-
-// rows of a ring: RING + 1, the last row mirrors row 0 so that word w+1 is always one row below word w
 
 // Returns (per lane) false if the stream needed more bits than n_words holds.
 template <int RING, int BATCH>
 __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
 {
-    constexpr uint32_t kBlock = RING / 2;               // words per refill
-    constexpr uint32_t kPerLane = kBlock / 32;          // words each lane loads per refill (1 or 2)
-    constexpr uint32_t kWant = kBlock;
-    constexpr uint32_t kUrgent = 3 + 4 * BATCH;         // lookahead + the batch in flight + the one before
-    static_assert(kUrgent < kBlock && (RING == 64 || RING == 128), "ring too small for the batch");
-    const int lane = lane_id();
-    uint32_t next_block = 0; // per lane: next block of MY stream to load
+    constexpr uint32_t kNeed = 3 + 4 * BATCH; // committed words a lane must have ahead at a boundary
+    static_assert(kNeed + 8 <= RING && (RING & (RING - 1)) == 0 && RING % 32 == 0, "ring too small for the batch");
+    uint32_t *rb = ring + lane_id();
+    // 16-byte view of the stream: vector v holds words [4v, 4v+4) counted from the aligned base
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(st.src);
+    const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    const uint32_t total = st.n_words ? st.n_words + skip : 0; // words from the aligned base
+    const uint32_t nvec = (total + 3) >> 2;
 
-    struct Fetch {
-        uint32_t v[kPerLane], w0; // this lane's words of the block, and the word index of v[0]
-        int owner;                // uniform
+    // fetch only ISSUES the load; nothing touches the value until commit, a batch later
+    auto fetch = [&](uint32_t w) -> uint4 { // words [w, w+4), w a multiple of 4
+        return (w >> 2) < nvec ? __ldg(vp + (w >> 2)) : make_uint4(0, 0, 0, 0);
     };
-    auto issue = [&](int owner) -> Fetch {
-        Fetch f;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(
-            shfl_u64(reinterpret_cast<unsigned long long>(st.src), owner));
-        const uint32_t nw = __shfl_sync(kFull, st.n_words, owner);
-        const uint32_t nb = __shfl_sync(kFull, next_block, owner);
-        f.owner = owner;
-        f.w0 = nb * kBlock + lane;
-#pragma unroll
-        for (uint32_t e = 0; e < kPerLane; e++)
-            f.v[e] = f.w0 + 32 * e < nw ? __ldg(src + f.w0 + 32 * e) : 0u;
-        if (lane == owner)
-            next_block++;
-        return f;
+    auto commit = [&](uint32_t w, const uint4 v) {
+        const uint32_t r = (w & (RING - 1)) * 32;
+        const uint32_t x = w + 0 < total ? v.x : 0u; // words past the stream's end read as zero
+        rb[r] = x;
+        rb[r + 32] = w + 1 < total ? v.y : 0u;
+        rb[r + 64] = w + 2 < total ? v.z : 0u;
+        rb[r + 96] = w + 3 < total ? v.w : 0u;
+        if (r == 0)
+            rb[RING * 32] = x; // mirror row: word w+1 is always one row below word w
     };
-    auto commit = [&](const Fetch &f) {
+    uint32_t loaded = 0;    // words [.., loaded) have been requested
+    uint32_t committed = 0; // words [.., committed) are in the ring
+    for (; loaded < RING; loaded += 32) { // initial fill, eight loads in flight at a time
+        uint4 f[8];
 #pragma unroll
-        for (uint32_t e = 0; e < kPerLane; e++) // column writes: 32-way bank conflict, off the parsers' path
-            ring[((f.w0 + 32 * e) & (RING - 1)) * 32 + f.owner] = f.v[e];
-        if ((f.w0 & (RING - 1)) == 0)
-            ring[RING * 32 + f.owner] = f.v[0]; // the mirror row
-    };
-    // initial fill: blocks 0 and 1 of every lane's stream, eight loads in flight at a time
-    for (int pass = 0; pass < 2; pass++) {
-        for (int base = 0; base < 32; base += 8) {
-            Fetch f[8];
+        for (int t = 0; t < 8; t++)
+            f[t] = fetch(loaded + 4 * t);
 #pragma unroll
-            for (int t = 0; t < 8; t++)
-                f[t] = issue(base + t);
-#pragma unroll
-            for (int t = 0; t < 8; t++)
-                commit(f[t]);
-        }
+        for (int t = 0; t < 8; t++)
+            commit(loaded + 4 * t, f[t]);
     }
-    __syncwarp();
+    committed = loaded;
 
-    const uint32_t *rb = ring + lane;
-    uint32_t pos = 0, i = 0, q_acc = 0;
+    uint32_t pos = skip * 32, i = 0, q_acc = 0;
     const uint32_t k = st.k, count = st.count;
     const uint32_t kshift = 31 - k; // payload = (brev(win) >> 1) >> (31 - k), valid for k = 0 too
     bool done = count == 0;
     int32_t o0 = 0, o1 = 0, o2 = 0;
     const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
-    Fetch pend[kRicePending];
-    int n_pend = 0; // uniform
+    uint4 pend0 = make_uint4(0, 0, 0, 0), pend1 = pend0;
+    uint32_t n_pend = 0; // per lane: 0, 1 or 2 vectors in flight, for words [committed, committed + 4*n_pend)
 
     while (true) {
-        // ---- batch boundary ----
-        if (n_pend) {
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < kRicePending; t++)
-                if (t < n_pend)
-                    commit(pend[t]);
-            n_pend = 0;
-            __syncwarp();
-        }
+        // ---- batch boundary (per-lane, predicated; the only vote is the exit test) ----
+        if (n_pend > 0)
+            commit(committed, pend0);
+        if (n_pend > 1)
+            commit(committed + 4, pend1);
+        committed += 4 * n_pend;
+        n_pend = 0;
         if (!__any_sync(kFull, !done))
             break;
-        unsigned urgent = __ballot_sync(kFull, !done && (pos >> 5) + kUrgent >= next_block * kBlock);
-        unsigned want = __ballot_sync(kFull, !done && (pos >> 5) + kWant >= next_block * kBlock) & ~urgent;
-        if (urgent | want) { // most boundaries have nothing to fetch
-#pragma unroll
-            for (int t = 0; t < kRicePending; t++) {
-                unsigned &from = urgent ? urgent : want;
-                if (from) {
-                    const int owner = __ffs(from) - 1;
-                    from &= from - 1;
-                    pend[t] = issue(owner);
-                    n_pend = t + 1;
-                }
-            }
+        const uint32_t wi = pos >> 5;
+        while (!done && committed < wi + kNeed) { // rare: this lane outran its top-up
+            commit(committed, fetch(committed));
+            committed += 4;
+            loaded = committed;
         }
-        if (urgent) { // more urgent requests than slots (rare): serve them synchronously
-            __syncwarp();
-            do {
-                const int owner = __ffs(urgent) - 1;
-                urgent &= urgent - 1;
-                commit(issue(owner));
-            } while (urgent);
-            __syncwarp();
+        if (!done && loaded + 4 <= wi + RING) { // room for one more vector without touching unread words
+            pend0 = fetch(loaded);
+            loaded += 4;
+            n_pend = 1;
+            if (loaded + 4 <= wi + RING) {
+                pend1 = fetch(loaded);
+                loaded += 4;
+                n_pend = 2;
+            }
         }
         // ---- BATCH parser steps: a whole symbol each, or 32 more ones of a long unary run ----
 #pragma unroll
@@ -353,7 +319,7 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
         if (rem > 1) st.out[b + 1] = o1;
         if (rem > 2) st.out[b + 2] = o2;
     }
-    return pos <= st.n_words * 32u;
+    return pos <= total * 32u;
 }
 
 } // namespace selab200

@@ -36,7 +36,7 @@ for tile in [t for t in (1, 4, 16, 48, 96) if t <= max_tile]:
     out = torch.empty(n_sub * 2048, dtype=torch.int32, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    for ring in (128, 64):
+    for ring in (64,):
         os.environ["SELAB200_RICE_RING"] = str(ring)
         def run():
             _lib.check(L.selab200_rice_decode_frames_device(d_descs.data_ptr(), n_frames * tile, 2, d_words.data_ptr(),

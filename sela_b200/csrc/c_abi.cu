@@ -249,16 +249,24 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     p.status = d_status;
     p.ws_q = static_cast<int32_t *>(d_ws);
     p.ws_res = reinterpret_cast<int32_t *>(static_cast<char *>(d_ws) + align256(n_sub * 128 * 4));
+    p.order_index = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(p.ws_res) + align256(n_sub * kFrame * 4));
+    const size_t n_slots = (n_sub + 12 + 3) / 4 * 4; // every class segment starts on a warp boundary
+    CUDA_TRY(cudaMemsetAsync(p.order_index, 0xff, n_slots * 4, stream));
+    k_decode_classify<<<1, 1024, 0, stream>>>(p);
+    if (int rc = launch_check("k_decode_classify"))
+        return rc;
     if (int rc = launch_rice_decode(p, 0, stream))
         return rc;
     if (int rc = launch_rice_decode(p, 1, stream))
         return rc;
     p.fallback_only = 1;
-    k_synthesise_quad<<<(unsigned)((n_sub + 3) / 4), 32, 0, stream>>>(p);
+    k_synthesise_quad<<<(unsigned)(n_slots / 4), 32, 0, stream>>>(p);
     if (int rc = launch_check("k_synthesise_quad"))
         return rc;
-    if (channels == 2)
-        return 0; // every stereo frame is handled by the batch kernel
+    if (channels == 2) { // every stereo frame is handled by the batch kernel + the difference fix-up
+        k_diff_fixup<<<n_frames, 128, 0, stream>>>(p);
+        return launch_check("k_diff_fixup");
+    }
     const size_t smem = synthesise_smem_bytes(channels);
     if (int rc = set_smem(k_synthesise, smem))
         return rc;
@@ -402,7 +410,7 @@ size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 size_t selab200_decode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 {
     const size_t n_sub = (size_t)n_frames * channels;
-    return align256(n_sub * 128 * 4) + align256(n_sub * kFrame * 4) + 256;
+    return align256(n_sub * 128 * 4) + align256(n_sub * kFrame * 4) + align256((n_sub + 16) * 4) + 256;
 }
 
 int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels,
@@ -464,6 +472,7 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
     p.status = d_status;
     p.ws_q = nullptr;
     p.ws_res = d_residues;
+    p.order_index = nullptr;
     p.fallback_only = 0;
     return launch_rice_decode(p, 1, (cudaStream_t)stream);
 }

@@ -312,6 +312,7 @@ struct DecodeParams {
     int32_t *status;
     int32_t *ws_q;   // [n_sub][128]
     int32_t *ws_res; // [n_sub][2048]
+    uint32_t *order_index; // [n_sub + 16]: subframe ids grouped by predictor-order class (k_decode_classify)
     int fallback_only;
 };
 
@@ -450,8 +451,91 @@ __global__ void k_synthesise(DecodeParams p)
     }
 }
 
-// K6, batch form: one warp = four consecutive subframes of the descriptor table (stereo: two
-// frames; mono: four frames; 8 channels: half a frame).  Handles every frame except those with
+// Predictor-order classes of the batch synthesis kernel: taps per lane (8 lanes per subframe)
+// 4 / 8 / 16, i.e. orders up to 28 / 56 / 112 (the last lane of a quarter must only hold taps
+// beyond the order).  A warp runs all four of its subframes with the taps of the largest order
+// among them, so subframes are first grouped by class: on the BASELINE synthetic (orders spread
+// evenly over 17..100) that removes about a quarter of the multiplies.
+__device__ __forceinline__ int order_class(int order) { return order <= 28 ? 0 : order <= 56 ? 1 : 2; }
+
+// One CTA: stable counting sort of the subframes by class into p.order_index; every class segment
+// starts on a warp boundary (4 subframes), gaps hold 0xffffffff (pre-set by the host side).
+__global__ void __launch_bounds__(1024) k_decode_classify(DecodeParams p)
+{
+    __shared__ unsigned long long warp_tot[32]; // four 16-bit class counts per warp
+    __shared__ uint32_t run[4];                 // next free unit slot per class
+    __shared__ uint32_t count[4];
+    const uint32_t gsz = 1;
+    const uint32_t n_units = p.n_frames * p.channels;
+    const int lane = lane_id(), warp = warp_id();
+    auto unit_class = [&](uint32_t u) {
+        int order = 0;
+        for (uint32_t j = 0; j < gsz; j++) {
+            const int o = p.descs[(size_t)u * gsz + j].lpc_order;
+            order = o > order ? o : order;
+        }
+        return order_class(order > kMaxOrder ? 0 : order);
+    };
+    if (threadIdx.x < 4)
+        count[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t mine[4] = {0, 0, 0, 0};
+    for (uint32_t u = threadIdx.x; u < n_units; u += 1024)
+        mine[unit_class(u)]++;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (mine[c])
+            atomicAdd(&count[c], mine[c]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t per_warp = 4 / gsz; // units per warp
+        uint32_t base = 0;
+        for (int c = 0; c < 4; c++) {
+            run[c] = base;
+            base += (count[c] + per_warp - 1) / per_warp * per_warp;
+        }
+    }
+    __syncthreads();
+    for (uint32_t tile = 0; tile < n_units; tile += 1024) {
+        const uint32_t u = tile + threadIdx.x;
+        const bool have = u < n_units;
+        const int c = have ? unit_class(u) : 0;
+        unsigned long long packed = have ? 1ull << (16 * c) : 0ull, incl = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(kFull, w, o);
+                if (lane >= o)
+                    w += t;
+            }
+            warp_tot[lane] = w; // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long before = (warp ? warp_tot[warp - 1] : 0ull) + incl - packed;
+        if (have) {
+            const uint32_t slot = run[c] + (uint32_t)((before >> (16 * c)) & 0xffffu);
+            for (uint32_t j = 0; j < gsz; j++)
+                p.order_index[(size_t)slot * gsz + j] = u * gsz + j;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4)
+            run[threadIdx.x] += (uint32_t)((warp_tot[31] >> (16 * threadIdx.x)) & 0xffffu);
+        __syncthreads();
+    }
+}
+
+// K6, batch form: one warp = four subframes of one predictor-order class (stereo: two whole
+// frames, the pair of a frame in neighbouring quarters).  Handles every frame except those with
 // difference-coded subframes and a channel count other than 2 (the reference's encoder never
 // produces those; k_synthesise above picks them up).
 struct QuadSmem {
@@ -467,7 +551,7 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
     const uint32_t ch = p.channels;
     const uint32_t n_sub = p.n_frames * ch;
     const int lane = lane_id(), q = lane >> 3, hl = lane & 7;
-    const uint32_t sub = blockIdx.x * 4 + q;
+    const uint32_t sub = p.order_index[blockIdx.x * 4 + q]; // grouped by order class; stereo pairs stay adjacent
     const bool exists = sub < n_sub;
     const uint32_t frame = exists ? sub / ch : 0, pos = exists ? sub % ch : 0;
 
@@ -504,7 +588,7 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
     // ---- predictors of the four subframes (warp-wide routines, one subframe at a time) ----
     for (int h = 0; h < 4; h++) {
         const int order_h = __shfl_sync(kFull, order, 8 * h);
-        const uint32_t sub_h = blockIdx.x * 4 + h;
+        const uint32_t sub_h = __shfl_sync(kFull, sub, 8 * h);
         CoefSmem &cf = sm.cf[h];
         for (int i = lane; i < 104; i += 32)
             cf.q[i] = i < order_h ? p.ws_q[(size_t)sub_h * 128 + i] : 0;
@@ -520,38 +604,54 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
     QuadIo io;
     io.res = p.ws_res + (size_t)(exists ? sub : 0) * kFrame;
     io.stage = &sm.stage[q][0][0];
-    const bool stereo = ch == 2;
     const bool diff = proc && mine.subframe_type == 1;
     const uint32_t channel = mine.channel;
     int16_t *out = p.pcm_out + (size_t)frame * kFrame * ch;
+    int32_t *row = p.ws_res + (size_t)(exists ? sub : 0) * kFrame;
     auto emit = [&](int B, int kx, int ky) {
-        if (stereo) {
-            // partner quarter holds the other channel of the same frame
-            const int px = __shfl_xor_sync(kFull, kx, 8), py = __shfl_xor_sync(kFull, ky, 8);
-            const int fx = diff ? px - kx : kx, fy = diff ? py - ky : ky; // frame_decoder.cpp:64-67
-            const int gx = __shfl_xor_sync(kFull, fx, 8), gy = __shfl_xor_sync(kFull, fy, 8);
-            if (proc && channel == 0) {
-                const uint32_t w0 = ((uint32_t)fx & 0xffffu) | ((uint32_t)gx << 16);
-                const uint32_t w1 = ((uint32_t)fy & 0xffffu) | ((uint32_t)gy << 16);
-                reinterpret_cast<uint2 *>(out)[(16 * B + 2 * hl) / 2] = make_uint2(w0, w1);
-            }
-        } else if (proc) {
-            const size_t t = 16 * B + 2 * hl;
+        if (!proc)
+            return;
+        const size_t t = 16 * B + 2 * hl;
+        if (diff) {
+            // a difference signal goes back into its (already consumed) residue row;
+            // k_diff_fixup turns it into parent - difference once the parent is complete
+            *reinterpret_cast<int2 *>(row + t) = make_int2(kx, ky);
+        } else {
             out[t * ch + channel] = (int16_t)(uint16_t)kx;
             out[(t + 1) * ch + channel] = (int16_t)(uint16_t)ky;
         }
     };
-    if (order_max <= 28)
-        warp_iir_quad<4>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
-    else if (order_max <= 56)
-        warp_iir_quad<8>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
-    else
-        warp_iir_quad<16>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit);
+    switch (order_class(order_max)) {
+    case 0: warp_iir_quad<4>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit); break;
+    case 1: warp_iir_quad<8>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit); break;
+    default: warp_iir_quad<16>(sm.cf[q], sm.ii[q], order, order_max, io, proc, emit); break;
+    }
 
     if (exists && !frame_ok) { // malformed frame: silence
         for (int t = hl; t < kFrame; t += 8)
             out[(size_t)t * ch + (pos < ch ? pos : 0)] = 0;
     }
+}
+
+// Difference reconstruction for stereo (frame_decoder.cpp:40-69): after k_synthesise_quad the
+// residue row of a difference-coded subframe holds the decoded difference; its channel is
+// parent - difference.  One CTA per frame; frames without a difference subframe return at once.
+__global__ void __launch_bounds__(128) k_diff_fixup(DecodeParams p)
+{
+    const uint32_t frame = blockIdx.x;
+    const selab200_subframe_desc *fd = p.descs + (size_t)frame * 2;
+    const selab200_subframe_desc d0 = fd[0], d1 = fd[1];
+    // same acceptance rules as the synthesis kernel (which has already reported any violation)
+    if (!desc_ok(d0, 2, p.n_words) || !desc_ok(d1, 2, p.n_words) || d0.channel == d1.channel)
+        return;
+    if ((d0.subframe_type | d1.subframe_type) == 0 || (d0.subframe_type & d1.subframe_type))
+        return; // nothing to do / both dependent (rejected upstream)
+    const uint32_t pos = d1.subframe_type ? 1 : 0;
+    const selab200_subframe_desc d = pos ? d1 : d0;
+    const int32_t *diff = p.ws_res + ((size_t)frame * 2 + pos) * kFrame;
+    int16_t *out = p.pcm_out + (size_t)frame * kFrame * 2;
+    for (int t = threadIdx.x; t < kFrame; t += blockDim.x)
+        out[2 * t + d.channel] = (int16_t)(uint16_t)((int)out[2 * t + d.parent_channel] - diff[t]);
 }
 
 inline size_t synthesise_smem_bytes(uint32_t ch)

@@ -618,8 +618,9 @@ __device__ void warp_iir_quad(const CoefSmem &cf, const IirSmem &ii, int order, 
     const unsigned long long steady = ii.pre[order];
     const bool writer = hl == 0;
     const int2 *r2 = reinterpret_cast<const int2 *>(io.res);
-    int2 rcur = has_res ? __ldg(r2 + hl) : make_int2(0, 0);
-    int2 rnext = has_res ? __ldg(r2 + 8 + hl) : make_int2(0, 0);
+    // plain loads: a difference subframe writes its result back into this row behind the reads
+    int2 rcur = has_res ? r2[hl] : make_int2(0, 0);
+    int2 rnext = has_res ? r2[8 + hl] : make_int2(0, 0);
     const int warm_blocks = order_max / 16 + 1; // blocks that contain some t <= order
     for (int B = 0; B < kFrame / 16; B++) {
         int32_t *row = io.stage + (B & 1) * 16;
@@ -629,7 +630,7 @@ __device__ void warp_iir_quad(const CoefSmem &cf, const IirSmem &ii, int order, 
             quad_block<TPL, false>(st, ii, order, steady, B, rcur, row, writer);
         rcur = rnext;
         if (B + 2 < kFrame / 16 && has_res)
-            rnext = __ldg(r2 + (B + 2) * 8 + hl);
+            rnext = r2[(B + 2) * 8 + hl];
         __syncwarp();
         const int2 kept = *reinterpret_cast<const int2 *>(row + 2 * hl);
         emit(B, kept.x, kept.y);

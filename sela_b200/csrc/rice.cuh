@@ -144,21 +144,26 @@ __device__ __noinline__ void warp_rice_pack(const int32_t *vals, int n, uint32_t
         uint32_t ones = u >> k;
         // "0 then the k payload bits MSB first" == bit-reversed low k bits, LSB first, after a zero
         const uint32_t tail = (k ? (__brev(u) >> (32 - k)) : 0u) << 1;
+        // Common case: the whole symbol (ones, the zero, the payload) fits one 32-bit piece.
+        // Otherwise the run of ones goes out 32 at a time and the rest follows.
         bool last;
         do {
             uint32_t bits, len;
-            last = ones == 0;
-            if (ones >= 32) {
+            if (ones + 1 + k <= 32) {
+                bits = (tail << ones) | ((1u << ones) - 1);
+                len = ones + 1 + k;
+                last = true;
+            } else if (ones >= 32) {
                 bits = 0xffffffffu;
                 len = 32;
-            } else if (ones) {
+                ones -= 32;
+                last = false;
+            } else {
                 bits = (1u << ones) - 1;
                 len = ones;
-            } else {
-                bits = tail;
-                len = 1 + k;
+                ones = 0;
+                last = false;
             }
-            ones -= last ? 0 : len;
             stage |= (unsigned long long)bits << fill;
             fill += len;
             if (fill >= 32) {

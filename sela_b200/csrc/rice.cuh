@@ -251,7 +251,7 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
     }
     committed = loaded;
 
-    uint32_t pos = skip * 32, i = 0, q_acc = 0;
+    uint32_t pos = skip * 32, i = 0, q_acc = 0, produced = 0;
     const uint32_t k = st.k, count = st.count;
     const uint32_t kshift = 31 - k; // payload = (brev(win) >> 1) >> (31 - k), valid for k = 0 too
     bool done = count == 0;
@@ -287,6 +287,12 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
             }
         }
         // ---- BATCH parser steps: a whole symbol each, or 32 more ones of a long unary run ----
+        // Two passes over the batch.  Pass 1 is the serial recurrence and nothing else:
+        //   pos -> LDS pair -> funnel shift -> clz -> pos'
+        // Pass 2 (payload bits, un-zig-zag, stores) has no dependence between steps, so its
+        // shared-memory latencies overlap instead of queueing behind the recurrence.
+        uint32_t p2s[BATCH], qs[BATCH];
+        bool emits[BATCH];
 #pragma unroll
         for (int s = 0; s < BATCH; s++) {
             const uint32_t ra = ((pos >> 5) & (RING - 1)) * 32;
@@ -294,28 +300,37 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
             const uint32_t ones = __clz(__brev(inv));  // 32 when the window is all ones
             const uint32_t run = ones >> 5;             // 1: no terminator in this window
             const uint32_t p2 = pos + ones + 1 - run;
-            const uint32_t rc = ((p2 >> 5) & (RING - 1)) * 32;
-            const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2);
-            const uint32_t payload = (__brev(win) >> 1) >> kshift;
             const uint32_t q = q_acc + ones;
-            const int32_t v = unzigzag((q << k) | payload); // uint32 shift as in rice_decoder.cpp:37
-            const bool emit = !done && !run;
+            p2s[s] = p2;
+            qs[s] = q;
+            emits[s] = !done && !run;
             if (!done) {
                 q_acc = run ? q : 0;
                 pos = run ? p2 : p2 + k;
             }
+            produced += emits[s];
+            done = done || produced == count;
+        }
+#pragma unroll
+        for (int s = 0; s < BATCH; s++) {
+            const uint32_t rc = ((p2s[s] >> 5) & (RING - 1)) * 32;
+            const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2s[s]);
+            const uint32_t payload = (__brev(win) >> 1) >> kshift;
+            const int32_t v = unzigzag((qs[s] << k) | payload); // uint32 shift as in rice_decoder.cpp:37
+            const bool emit = emits[s];
             const uint32_t sel = i & 3u;
             if (vec_out) {
                 if (emit && sel == 3)
                     *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
-                o0 = sel == 0 ? v : o0;
-                o1 = sel == 1 ? v : o1;
-                o2 = sel == 2 ? v : o2;
+                if (emit) {
+                    o0 = sel == 0 ? v : o0;
+                    o1 = sel == 1 ? v : o1;
+                    o2 = sel == 2 ? v : o2;
+                }
             } else if (emit) {
                 st.out[i] = v;
             }
             i += emit;
-            done = done || i == count;
         }
     }
     if (vec_out && count) {

@@ -110,6 +110,20 @@ def measured_traffic(kernel):
         return None
 
 
+_REAL_STDOUT = []
+
+
+def emit_line(line):
+    """Print the result line on the process's real stdout (see the fd juggling around NCCL init)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT[0], data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def make_pcm(seed):
     from sela_b200 import synth
     return synth.sine_noise(SAMPLE_RATE, CHANNELS, seconds=SECONDS, seed=seed)
@@ -164,7 +178,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": info["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -180,9 +194,12 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # rank 0's stdout must carry exactly ONE line (the JSON): keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0's stdout must carry exactly ONE line (the JSON), but NCCL writes its version banner
+        # to fd 1 when the first communicator comes up: park the real stdout and point fd 1 at stderr
+        # until the line is ready (emit_line)
+        sys.stdout.flush()
+        _REAL_STDOUT.append(os.dup(1))
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi is slow to spin up
@@ -313,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
             descs_gpu = codec.descs.cpu().numpy().view(_lib.DESC_DTYPE)[: sf * CHANNELS]
             words_gpu = codec.words[: int(descs_gpu[-1]["res_offset"]) + int(descs_gpu[-1]["res_words"])].cpu().numpy().view(np.uint32)
             line["bit_exact_vs_cpu"] = bool(descs_gpu.tobytes() == d_ref.tobytes() and np.array_equal(words_gpu, w_ref))
-        print(json.dumps(line))
+        emit_line(line)
     for p in (p1, p2, p3, p4):
         L.selab200_host_free(p)
     if dist:

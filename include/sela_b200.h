@@ -120,7 +120,9 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
  * `stream` (a cudaStream_t; NULL is the legacy default stream, as everywhere in CUDA) and the call
  * returns without synchronising.  d_status (int32, device) receives 0 or a
  * selab200_status once the stream has drained; d_words_used is a device uint64.
- * workspace: selab200_*_workspace_bytes() bytes of device memory, 256-aligned. */
+ * workspace: selab200_*_workspace_bytes() bytes of device memory, 256-aligned.  d_words must be
+ * 16-byte aligned and readable up to the next 16-byte boundary past its last word (the Rice
+ * decoder fetches 16 bytes at a time); cudaMalloc / torch allocations satisfy both. */
 size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels);
 int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels,
                                   selab200_subframe_desc *d_descs, uint32_t *d_words,

@@ -334,3 +334,28 @@ def test_rice_streams_with_long_unary_runs_and_k_extremes(O):
     out = sela_b200.rice_decode(words, nw, k, counts, out_stride=2048)
     for i, c in enumerate(cases):
         assert np.array_equal(out[i, :c.size], c), i
+
+
+def test_full_baseline_config2_config3_bit_exact(O):
+    """BASELINE configs[1]/[2] at FULL size (44.1 kHz stereo, 10 min, 12 919 frames): the whole
+    descriptor table and word arena against the CPU coder, then decode and compare with both the
+    CPU decoder's output and the source."""
+    pcm = synth.sine_noise(44100, 2, seconds=600, seed=1)
+    d, w = sela_b200.encode_frames(pcm, 2)
+    d_ref, w_ref = O.encode_frames(pcm, 2)
+    assert d.shape == d_ref.shape == (12919 * 2,)
+    assert d.tobytes() == d_ref.tobytes()
+    assert np.array_equal(w, w_ref)
+    out = sela_b200.decode_frames(d, w, 2)
+    assert np.array_equal(out, pcm.reshape(-1))
+    assert np.array_equal(out, O.decode_frames(d_ref, w_ref, 2))
+
+
+def test_config4_shape_bit_exact(O):
+    """BASELINE configs[3] shape (48 kHz, 8 channels), two minutes of it."""
+    pcm = synth.sine_noise(48000, 8, seconds=120, seed=2)
+    d, w = sela_b200.encode_frames(pcm, 8)
+    d_ref, w_ref = O.encode_frames(pcm, 8)
+    assert d.tobytes() == d_ref.tobytes() and np.array_equal(w, w_ref)
+    assert not d["subframe_type"].any()          # more than two channels: no difference coding
+    assert np.array_equal(sela_b200.decode_frames(d, w, 8), pcm.reshape(-1))

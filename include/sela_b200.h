@@ -143,6 +143,56 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
                                        uint32_t channels, const uint32_t *d_words, size_t n_words,
                                        int32_t *d_residues, int32_t *d_status, void *stream);
 
+/* ------------------------------------------------ .sela container level -- */
+
+/* The byte-packed file format of file::SelaFile (src/file/sela_file.cpp:19-137): 15-byte header
+ * ("SeLa", sampleRate u32, bitsPerSample u16, channels u8, numFrames u32, little endian), then
+ * per frame the sync word 0xAA55FF00 and per subframe
+ *   channel, type, parent, reflK (u8), reflInts (u16), order (u8), refl words,
+ *   resK (u8), resInts (u16), samples (u16), residue words.
+ * These entry points move whole containers: the encoder's gather kernel writes the byte stream
+ * in place (headers included), the decoder realigns the word arrays on the device, so the host
+ * never builds per-subframe vectors.  Bytes are identical to what
+ * file::SelaFile::writeToFile emits for the frames selab200_encode_frames returns. */
+typedef struct selab200_container_info {
+    uint32_t sample_rate;
+    uint16_t bits_per_sample;
+    uint8_t  channels;
+    uint8_t  reserved;
+    uint32_t header_frames;  /* the numFrames field                                            */
+    uint32_t n_frames;       /* frames present: the walk stops quietly at the first bad sync
+                                word, as the reference reader does (sela_file.cpp:48-56)       */
+    uint64_t n_words;        /* Rice words of those frames                                     */
+    uint64_t n_bytes_used;   /* bytes of the container those frames (and the header) occupy    */
+} selab200_container_info;
+
+/* Worst-case container size for n_frames x channels subframes of 16-bit audio. */
+size_t selab200_container_bound(uint32_t n_frames, uint32_t channels);
+
+/* WAV data chunk -> complete .sela byte stream: sela::Encoder::process + file::SelaFile::writeToFile
+ * (src/sela/encoder.cpp:94-99, src/file/sela_file.cpp:105-137).  pcm as in selab200_encode_frames.
+ * SELAB200_ERR_CAPACITY if `capacity` bytes do not suffice (*bytes_used = the size needed). */
+int selab200_encode_container(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
+                              uint32_t sample_rate, uint16_t bits_per_sample,
+                              uint8_t *container, size_t capacity, size_t *bytes_used);
+
+/* Host-only parse of a container (no device needed): header fields and the frame walk of
+ * file::SelaFile::readFromFile (src/file/sela_file.cpp:19-103).  Errors (SELAB200_ERR_BITSTREAM)
+ * carry the message the host mirror throws for the same file: too small, bad magic, truncated. */
+int selab200_container_info_get(const uint8_t *container, size_t n_bytes, selab200_container_info *info);
+
+/* Complete .sela byte stream -> interleaved int16 PCM (the WAV data chunk):
+ * file::SelaFile::readFromFile + sela::Decoder::processFrames.  open: parses the header, starts
+ * the upload and walks the frame headers on the host meanwhile (the walk is a pointer chase
+ * through the byte stream -- inherently serial, microseconds per thousand frames; everything
+ * that touches the payload runs on the device).  `container` must stay valid until close.
+ * decode: pcm_out receives info.n_frames * channels * 2048 samples. */
+typedef struct selab200_container selab200_container;
+int  selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_container **handle,
+                             selab200_container_info *info);
+int  selab200_container_decode(selab200_container *handle, int16_t *pcm_out);
+void selab200_container_close(selab200_container *handle);
+
 /* ------------------------------------------ stage level (host buffers) -- */
 
 /* lpc::ResidueGenerator::process (src/lpc/residue_generator.cpp:121-134) for

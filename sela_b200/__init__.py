@@ -4,5 +4,6 @@ CUDA kernels (sm_100a) behind the C ABI of include/sela_b200.h; this package hol
 the kernels (csrc/), the C++ mirror of the reference interface (host/) and a thin
 Python mirror used by the tests and bench.py.  No CPU fallback.
 """
-from .codec import (DESC_DTYPE, FRAME, SelaB200Error, decode_frames, encode_frames, init,  # noqa: F401
-                    lpc_residues, lpc_samples, rice_decode, rice_encode)
+from .codec import (DESC_DTYPE, FRAME, SelaB200Error, container_info, decode_container,  # noqa: F401
+                    decode_frames, encode_container, encode_frames, init, lpc_residues, lpc_samples,
+                    rice_decode, rice_encode)

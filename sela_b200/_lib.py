@@ -25,6 +25,13 @@ DESC_DTYPE = np.dtype([
 ], align=True)
 assert DESC_DTYPE.itemsize == 32
 
+# mirrors selab200_container_info
+INFO_DTYPE = np.dtype([
+    ("sample_rate", "<u4"), ("bits_per_sample", "<u2"), ("channels", "u1"), ("reserved", "u1"),
+    ("header_frames", "<u4"), ("n_frames", "<u4"), ("n_words", "<u8"), ("n_bytes_used", "<u8"),
+], align=True)
+assert INFO_DTYPE.itemsize == 32
+
 STATUS_NAMES = {0: "OK", -1: "NO_DEVICE", -2: "CUDA", -3: "ARGUMENT", -4: "CAPACITY", -5: "RANGE",
                 -6: "BITSTREAM", -7: "NOT_INIT"}
 
@@ -55,6 +62,12 @@ _SIGNATURES = {
     "selab200_decode_workspace_bytes": (_SZ, [_U32, _U32]),
     "selab200_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V, _SZ, _V]),
     "selab200_rice_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V]),
+    "selab200_container_bound": (_SZ, [_U32, _U32]),
+    "selab200_encode_container": (_I, [_V, _U32, _U32, _U32, C.c_uint16, _V, _SZ, _V]),
+    "selab200_container_info_get": (_I, [_V, _SZ, _V]),
+    "selab200_container_open": (_I, [_V, _SZ, _V, _V]),
+    "selab200_container_decode": (_I, [_V, _V]),
+    "selab200_container_close": (None, [_V]),
     "selab200_lpc_residues": (_I, [_V, _U32, _V, _V, _V]),
     "selab200_lpc_samples": (_I, [_V, _U32, _V, _V, _V]),
     "selab200_rice_encode": (_I, [_V, _V, _U32, _U32, _V, _V, _V, _U32]),

@@ -7,6 +7,10 @@ error behaviour as in include/sela_b200.h):
                                     (= frame::FrameEncoder/FrameDecoder::process per frame)
     lpc_residues / lpc_samples      lpc::ResidueGenerator / lpc::SampleGenerator ::process
     rice_encode / rice_decode       rice::RiceEncoder / rice::RiceDecoder ::process
+    encode_container / decode_container / container_info
+                                    sela::Encoder::process + file::SelaFile::writeToFile, and
+                                    file::SelaFile::readFromFile + sela::Decoder::processFrames,
+                                    on the byte-packed .sela stream
 
 Everything computes on the GPU through the C ABI; NumPy only carries host buffers.
 The C++ mirror of the same interface (data::, frame::, file::, sela:: classes and
@@ -17,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import DESC_DTYPE, FRAME, MAX_ORDER, SelaB200Error, check, init, lib  # noqa: F401
+from ._lib import DESC_DTYPE, FRAME, INFO_DTYPE, MAX_ORDER, SelaB200Error, check, init, lib  # noqa: F401
 
 
 def _c(a, dtype):
@@ -113,3 +117,44 @@ def rice_decode(words, n_words, k, counts, out_stride=None, device=0):
     check(lib().selab200_rice_decode(words.ctypes.data, n_words.ctypes.data, words_stride, k.ctypes.data,
                                      counts.ctypes.data, n, out.ctypes.data, out_stride))
     return out
+
+
+def encode_container(pcm, channels, sample_rate, bits_per_sample=16, capacity=None, device=0):
+    """int16 interleaved PCM (whole frames) -> the bytes of the .sela file (uint8 array)."""
+    init(device)
+    pcm = _c(pcm, np.int16).reshape(-1)
+    n_frames = pcm.size // (FRAME * channels)
+    if n_frames * FRAME * channels != pcm.size:
+        raise ValueError("pcm must hold whole 2048-sample frames")
+    L = lib()
+    cap = capacity if capacity is not None else L.selab200_container_bound(n_frames, channels)
+    out = np.empty(max(cap, 1), np.uint8)
+    used = C.c_size_t(0)
+    check(L.selab200_encode_container(pcm.ctypes.data, n_frames, channels, sample_rate, bits_per_sample,
+                                      out.ctypes.data, cap, C.addressof(used)))
+    return out[:used.value].copy()
+
+
+def container_info(container):
+    """Header fields and frame walk of a .sela byte stream (host only, no device needed)."""
+    buf = _c(np.frombuffer(container, np.uint8) if isinstance(container, (bytes, bytearray)) else container, np.uint8)
+    info = np.zeros(1, INFO_DTYPE)
+    check(lib().selab200_container_info_get(buf.ctypes.data, buf.size, info.ctypes.data))
+    return {k: int(info[0][k]) for k in INFO_DTYPE.names if k != "reserved"}
+
+
+def decode_container(container, device=0):
+    """.sela byte stream -> (info dict, int16 interleaved PCM of info['n_frames'] frames)."""
+    init(device)
+    buf = _c(np.frombuffer(container, np.uint8) if isinstance(container, (bytes, bytearray)) else container, np.uint8)
+    L = lib()
+    info = np.zeros(1, INFO_DTYPE)
+    handle = C.c_void_p(0)
+    check(L.selab200_container_open(buf.ctypes.data, buf.size, C.addressof(handle), info.ctypes.data))
+    try:
+        n = int(info[0]["n_frames"]) * int(info[0]["channels"]) * FRAME
+        pcm = np.empty(n, np.int16)
+        check(L.selab200_container_decode(handle, pcm.ctypes.data))
+    finally:
+        L.selab200_container_close(handle)
+    return {k: int(info[0][k]) for k in INFO_DTYPE.names if k != "reserved"}, pcm

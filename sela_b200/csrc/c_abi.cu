@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -133,6 +134,10 @@ int require_ready()
 {
     if (!g.ready)
         return fail(SELAB200_ERR_NOT_INIT, "selab200_init() has not been called (or found no CUDA device)");
+    // the current device is per host thread; callers may arrive on a thread other than init()'s
+    cudaError_t e = cudaSetDevice(g.device);
+    if (e != cudaSuccess)
+        return fail(SELAB200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g.device, cudaGetErrorString(e));
     return 0;
 }
 
@@ -162,7 +167,8 @@ int launch_check(const char *what)
 int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *d_descs,
                   uint32_t *d_words, size_t capacity, uint64_t *d_used, int32_t *d_status, void *d_ws,
                   size_t ws_bytes, cudaStream_t stream, bool fresh = true, cudaEvent_t before_scan = nullptr,
-                  cudaEvent_t after_scan = nullptr, unsigned long long *h_fill_after = nullptr)
+                  cudaEvent_t after_scan = nullptr, unsigned long long *h_fill_after = nullptr,
+                  uint8_t *d_container = nullptr, unsigned long long sub_base = 0)
 {
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
@@ -213,6 +219,10 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
         CUDA_TRY(cudaMemcpyAsync(h_fill_after, d_used, 8, cudaMemcpyDeviceToHost, stream));
     if (after_scan)
         CUDA_TRY(cudaEventRecord(after_scan, stream));
+    if (d_container) { // byte-packed .sela stream instead of the word arena
+        k_encode_gather_container<<<(unsigned)((n_sub + 7) / 8), 256, 0, stream>>>(p, d_container, sub_base);
+        return launch_check("k_encode_gather_container");
+    }
     k_encode_gather<<<(unsigned)((n_sub + 7) / 8), 256, 0, stream>>>(p);
     return launch_check("k_encode_gather");
 }
@@ -477,17 +487,18 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
     return launch_rice_decode(p, 1, (cudaStream_t)stream);
 }
 
-int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
-                           selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
-                           size_t *words_used)
+// Bytes of container in front of frame f when `words` Rice words precede it.
+static unsigned long long container_frame_byte(unsigned long long f, uint32_t channels, unsigned long long words)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
-        return rc;
-    if (!pcm || !descs || !words || !words_used)
-        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
-    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
-        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    return kContainerHeaderBytes + 4 * f + (unsigned long long)kSubframeHeaderBytes * f * channels + 4 * words;
+}
+
+// The pipelined encoder over host buffers.  Two output forms: descriptors + word arena
+// (descs/words), or the byte-packed container (`container`, descs == words == nullptr) whose
+// device image lives in g.words.
+static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *descs,
+                       uint32_t *words, size_t words_capacity, size_t *words_used, uint8_t *container)
+{
     *words_used = 0;
     if (n_frames == 0)
         return 0;
@@ -499,7 +510,7 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
     const size_t ws_bytes = selab200_encode_workspace_bytes(cf, channels);
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
-    if (int rc = g.words.ensure(words_capacity * 4 + 16)) return rc;
+    if (int rc = g.words.ensure(container_frame_byte(n_frames, channels, words_capacity) + 64)) return rc;
     constexpr int kEncLanes = 2;
     for (int i = 0; i < kEncLanes && (uint32_t)i < n_chunks; i++)
         if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
@@ -523,7 +534,9 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
         CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
         if (int rc = encode_device(d_pcm + (size_t)f0 * channels * kFrame, nf, channels, d_descs + (size_t)f0 * channels,
                                    d_words, words_capacity, d_used, d_status, ws.ptr, ws.bytes, cs, false,
-                                   c ? g.ev_scan[c - 1] : nullptr, g.ev_scan[c], &g.h_totals[c + 1]))
+                                   c ? g.ev_scan[c - 1] : nullptr, g.ev_scan[c], &g.h_totals[c + 1],
+                                   container ? static_cast<uint8_t *>(g.words.ptr) : nullptr,
+                                   (unsigned long long)f0 * channels))
             return rc;
         CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
     }
@@ -534,6 +547,13 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
         const unsigned long long lo = g.h_totals[c], hi = g.h_totals[c + 1];
         if (hi > words_capacity || hi < lo)
             break; // capacity exceeded: reported through the status word below
+        if (container) {
+            const unsigned long long b0 = container_frame_byte(f0, channels, lo);
+            const unsigned long long b1 = container_frame_byte(f0 + nf, channels, hi);
+            CUDA_TRY(cudaMemcpyAsync(container + b0, static_cast<uint8_t *>(g.words.ptr) + b0, b1 - b0,
+                                     cudaMemcpyDeviceToHost, g.s_d2h));
+            continue;
+        }
         CUDA_TRY(cudaMemcpyAsync(descs + (size_t)f0 * channels, d_descs + (size_t)f0 * channels,
                                  (size_t)nf * channels * sizeof(selab200_subframe_desc), cudaMemcpyDeviceToHost,
                                  g.s_d2h));
@@ -549,6 +569,51 @@ int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t chann
     if (g.h_small[0] != 0)
         return fail(g.h_small[0], "%s", status_text(g.h_small[0]));
     return 0;
+}
+
+int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
+                           selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
+                           size_t *words_used)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!pcm || !descs || !words || !words_used)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    return encode_host(pcm, n_frames, channels, descs, words, words_capacity, words_used, nullptr);
+}
+
+size_t selab200_container_bound(uint32_t n_frames, uint32_t channels)
+{
+    return (size_t)container_frame_byte(n_frames, channels, selab200_encode_words_bound(n_frames, channels));
+}
+
+int selab200_encode_container(const int16_t *pcm, uint32_t n_frames, uint32_t channels, uint32_t sample_rate,
+                              uint16_t bits_per_sample, uint8_t *container, size_t capacity, size_t *bytes_used)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if ((!pcm && n_frames) || !container || !bytes_used)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    const unsigned long long fixed = container_frame_byte(n_frames, channels, 0);
+    *bytes_used = (size_t)fixed;
+    if (capacity < fixed)
+        return fail(SELAB200_ERR_CAPACITY, "container buffer too small: %zu bytes, need more than %llu", capacity, fixed);
+    // file::SelaFile::writeToFile, header part (src/file/sela_file.cpp:107-112)
+    const uint8_t header[15] = {'S', 'e', 'L', 'a',
+                                (uint8_t)sample_rate, (uint8_t)(sample_rate >> 8), (uint8_t)(sample_rate >> 16), (uint8_t)(sample_rate >> 24),
+                                (uint8_t)bits_per_sample, (uint8_t)(bits_per_sample >> 8), (uint8_t)channels,
+                                (uint8_t)n_frames, (uint8_t)(n_frames >> 8), (uint8_t)(n_frames >> 16), (uint8_t)(n_frames >> 24)};
+    memcpy(container, header, sizeof header);
+    size_t words_used = 0;
+    const int rc = encode_host(pcm, n_frames, channels, nullptr, nullptr, (size_t)((capacity - fixed) / 4), &words_used, container);
+    *bytes_used = (size_t)container_frame_byte(n_frames, channels, words_used);
+    return rc;
 }
 
 int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
@@ -610,6 +675,243 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
         DeviceBuffer &ws = g.lane_work[c % kLanes];
         CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[c], 0));
         if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_words, n_words,
+                                   d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))
+            return rc;
+        CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
+        CUDA_TRY(cudaStreamWaitEvent(g.s_d2h, g.ev_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(pcm_out + (size_t)f0 * channels * kFrame, d_pcm + (size_t)f0 * channels * kFrame,
+                                 nf * frame_bytes, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    return read_status(g.s_d2h, d_status);
+}
+
+// ---- .sela container, decode side ----------------------------------------------------------
+
+} // extern "C"
+
+struct selab200_container {
+    const uint8_t *bytes = nullptr;
+    size_t n_bytes = 0;
+    selab200_container_info info{};
+    selab200_subframe_desc *h_descs = nullptr; // pinned, info.n_frames * channels
+    void *d_bytes = nullptr;                   // device image of the container (+ padding)
+    static constexpr int kPieces = 8;
+    cudaEvent_t ev_piece[kPieces] = {};
+    size_t piece_bytes = 0;
+    int n_pieces = 0;
+};
+
+namespace {
+
+// file::SelaFile::readFromFile (src/file/sela_file.cpp:19-103) without the copies: validates the
+// header, then hops from frame to frame.  With `descs` it also emits one descriptor per subframe,
+// arena offsets assigned in file order.  Messages match the host mirror's reader.
+int walk_container(const uint8_t *b, size_t n, selab200_container_info *info,
+                   std::vector<selab200_subframe_desc> *descs)
+{
+    memset(info, 0, sizeof *info);
+    if (n < 15)
+        return fail(SELAB200_ERR_BITSTREAM, "File is too small, probably not a sela file.");
+    if (memcmp(b, "SeLa", 4) != 0)
+        return fail(SELAB200_ERR_BITSTREAM, "Magic number is incorrect, probably not a sela file.");
+    auto u16 = [&](size_t o) { return (uint32_t)b[o] | ((uint32_t)b[o + 1] << 8); };
+    auto u32 = [&](size_t o) { return u16(o) | (u16(o + 2) << 16); };
+    info->sample_rate = u32(4);
+    info->bits_per_sample = (uint16_t)u16(8);
+    info->channels = b[10];
+    info->header_frames = u32(11);
+    const uint32_t channels = info->channels;
+    size_t at = 15;
+    unsigned long long words = 0;
+    uint32_t f = 0;
+    for (; f < info->header_frames; f++) {
+        if (at + 4 > n || u32(at) != 0xAA55FF00u)
+            break;
+        at += 4;
+        for (uint32_t c = 0; c < channels; c++) {
+            if (at + 7 > n)
+                return fail(SELAB200_ERR_BITSTREAM, "sela file is truncated");
+            const uint32_t refl_words = u16(at + 4);
+            const size_t at2 = at + 7 + 4 * (size_t)refl_words;
+            if (at2 + 5 > n)
+                return fail(SELAB200_ERR_BITSTREAM, "sela file is truncated");
+            const uint32_t res_words = u16(at2 + 1);
+            if (at2 + 5 + 4 * (size_t)res_words > n)
+                return fail(SELAB200_ERR_BITSTREAM, "sela file is truncated");
+            if (descs) {
+                selab200_subframe_desc d;
+                d.channel = b[at];
+                d.subframe_type = b[at + 1];
+                d.parent_channel = b[at + 2];
+                d.refl_rice_param = b[at + 3];
+                d.refl_words = (uint16_t)refl_words;
+                d.lpc_order = b[at + 6];
+                d.res_rice_param = b[at2];
+                d.res_words = (uint16_t)res_words;
+                d.samples = (uint16_t)u16(at2 + 3);
+                d.reserved = 0;
+                d.refl_offset = words;
+                d.res_offset = words + refl_words;
+                descs->push_back(d);
+            }
+            words += refl_words + res_words;
+            at = at2 + 5 + 4 * (size_t)res_words;
+        }
+    }
+    info->n_frames = f;
+    info->n_words = words;
+    info->n_bytes_used = at;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int selab200_container_info_get(const uint8_t *container, size_t n_bytes, selab200_container_info *info)
+{
+    if (!container || !info)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    return walk_container(container, n_bytes, info, nullptr);
+}
+
+void selab200_container_close(selab200_container *h)
+{
+    if (!h)
+        return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g.s_h2d)
+        cudaStreamSynchronize(g.s_h2d); // the upload reads the caller's bytes
+    for (cudaEvent_t e : h->ev_piece)
+        if (e)
+            cudaEventDestroy(e);
+    if (h->d_bytes)
+        cudaFree(h->d_bytes);
+    if (h->h_descs)
+        cudaFreeHost(h->h_descs);
+    delete h;
+}
+
+int selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_container **handle,
+                            selab200_container_info *info)
+{
+    if (!container || !handle || !info)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    *handle = nullptr;
+    selab200_container_info probe;
+    if (int rc = walk_container(container, n_bytes < 15 ? n_bytes : 15, &probe, nullptr)) // header checks only
+        return rc;
+    selab200_container *h = nullptr;
+    int rc = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if ((rc = require_ready()) != 0)
+            return rc;
+        h = new selab200_container;
+        h->bytes = container;
+        h->n_bytes = n_bytes;
+        // start the upload first: the DMA engine streams the bytes while this thread walks them
+        cudaError_t e = cudaMalloc(&h->d_bytes, n_bytes + 64);
+        if (e != cudaSuccess)
+            rc = fail(SELAB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n_bytes + 64, cudaGetErrorString(e));
+        h->piece_bytes = ((n_bytes + selab200_container::kPieces - 1) / selab200_container::kPieces + 255) & ~(size_t)255;
+        for (int i = 0; rc == 0 && (size_t)i * h->piece_bytes < n_bytes; i++) {
+            const size_t lo = (size_t)i * h->piece_bytes;
+            const size_t len = lo + h->piece_bytes <= n_bytes ? h->piece_bytes : n_bytes - lo;
+            e = cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(static_cast<uint8_t *>(h->d_bytes) + lo, container + lo, len, cudaMemcpyHostToDevice, g.s_h2d);
+            if (e == cudaSuccess)
+                e = cudaEventRecord(h->ev_piece[i], g.s_h2d);
+            if (e != cudaSuccess)
+                rc = fail(SELAB200_ERR_CUDA, "container upload failed: %s", cudaGetErrorString(e));
+            h->n_pieces = i + 1;
+        }
+    }
+    if (rc == 0) {
+        // One walk, into a growing host vector (numFrames is not trusted for sizing), then a pinned copy
+        // the chunked descriptor uploads can stream from.
+        std::vector<selab200_subframe_desc> descs;
+        descs.reserve(n_bytes / 2048 + 16);
+        rc = walk_container(container, n_bytes, &h->info, &descs);
+        if (rc == 0 && !descs.empty()) {
+            const size_t bytes = descs.size() * sizeof(selab200_subframe_desc);
+            if (cudaMallocHost(reinterpret_cast<void **>(&h->h_descs), bytes) != cudaSuccess)
+                rc = fail(SELAB200_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+            else
+                memcpy(h->h_descs, descs.data(), bytes);
+        }
+    }
+    if (rc != 0) {
+        char keep[sizeof g_error];
+        memcpy(keep, g_error, sizeof keep);
+        selab200_container_close(h);
+        memcpy(g_error, keep, sizeof keep);
+        return rc;
+    }
+    *info = h->info;
+    *handle = h;
+    return 0;
+}
+
+int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!h)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    const uint32_t n_frames = h->info.n_frames, channels = h->info.channels;
+    if (n_frames == 0)
+        return 0;
+    if (!pcm_out)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    PipelineDrain drain;
+    const uint32_t cf = chunk_frames_for(n_frames, 8);
+    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
+    const size_t n_sub = (size_t)n_frames * channels;
+    const size_t frame_bytes = (size_t)channels * kFrame * 2;
+    const size_t ws_bytes = selab200_decode_workspace_bytes(cf, channels);
+    const size_t n_words = (size_t)h->info.n_words;
+    if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
+    if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
+    if (int rc = g.words.ensure(n_words * 4 + 64)) return rc;
+    for (int i = 0; i < kLanes && (uint32_t)i < n_chunks; i++)
+        if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
+    selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
+    uint32_t *d_arena = static_cast<uint32_t *>(g.words.ptr);
+    const uint8_t *d_bytes = static_cast<const uint8_t *>(h->d_bytes);
+
+    CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
+    CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
+    for (int i = 1; i < kLanes; i++)
+        CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        const selab200_subframe_desc *dc = h->h_descs + (size_t)f0 * channels;
+        const size_t chunk_sub = (size_t)nf * channels;
+        cudaStream_t cs = g.s_compute[c % kLanes];
+        DeviceBuffer &ws = g.lane_work[c % kLanes];
+        // descriptors go up on the chunk's own lane: s_h2d is still busy with the container pieces
+        CUDA_TRY(cudaMemcpyAsync(d_descs + (size_t)f0 * channels, dc, chunk_sub * sizeof(*dc), cudaMemcpyHostToDevice, cs));
+        // the container bytes this chunk reads end with its last subframe (+3 bytes of slack)
+        const selab200_subframe_desc &last = dc[chunk_sub - 1];
+        const unsigned long long end_byte =
+            container_frame_byte(f0 + nf, channels, last.res_offset + last.res_words) + 3;
+        int piece = (int)(end_byte / h->piece_bytes);
+        if (piece >= h->n_pieces)
+            piece = h->n_pieces - 1;
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->ev_piece[piece], 0));
+        k_container_unpack<<<(unsigned)((chunk_sub + 7) / 8), 256, 0, cs>>>(d_bytes, d_descs + (size_t)f0 * channels,
+                                                                           (uint32_t)chunk_sub, channels,
+                                                                           (unsigned long long)f0 * channels, d_arena);
+        if (int rc = launch_check("k_container_unpack"))
+            return rc;
+        if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_arena, n_words,
                                    d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))
             return rc;
         CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));

@@ -291,6 +291,119 @@ __global__ void __launch_bounds__(256) k_encode_gather(EncodeParams p)
         dst[w] = slot[w];
 }
 
+// --------------------------------------------------------------- container --
+//
+// The .sela container (src/file/sela_file.cpp:105-137) is byte-packed: a 15-byte file header,
+// then per frame the sync word 0xAA55FF00 (little endian: 00 FF 55 AA) and per subframe
+//   channel, type, parent, reflK (u8 each), reflInts (u16), order (u8), refl words,
+//   resK (u8), resInts (u16), samples (u16), residue words.
+// With the word arena laid out in file order (refl words then residue words, subframe after
+// subframe), the byte position of everything follows from the subframe's global index g, its
+// frame f = g / channels and the arena offset W of its first word:
+//   header of g at  15 + 4*(f+1) + 12*g + 4*W.
+// Word arrays therefore sit at arbitrary byte alignments; the kernels below move them with
+// aligned 32-bit accesses and a funnel shift, byte stores only at the two ragged ends.
+constexpr unsigned long long kContainerHeaderBytes = 15;
+constexpr uint32_t kSubframeHeaderBytes = 12;
+
+__device__ __forceinline__ unsigned long long container_subframe_byte(unsigned long long g, uint32_t channels,
+                                                                       unsigned long long first_word)
+{
+    return kContainerHeaderBytes + 4ull * (g / channels + 1) + (unsigned long long)kSubframeHeaderBytes * g +
+           4ull * first_word;
+}
+
+// n words from src (aligned) to byte address out + D (any alignment).
+__device__ __forceinline__ void put_words_at_byte(uint8_t *out, unsigned long long D, const uint32_t *src, uint32_t n)
+{
+    const int lane = lane_id();
+    if (n == 0)
+        return;
+    const uint32_t s = (uint32_t)(D & 3);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (D - s));
+    if (s == 0) {
+        for (uint32_t t = lane; t < n; t += 32)
+            dst[t] = src[t];
+        return;
+    }
+    for (uint32_t t = 1 + lane; t < n; t += 32) // aligned word t = high bytes of src[t-1], low bytes of src[t]
+        dst[t] = __funnelshift_l(src[t - 1], src[t], 8 * s);
+    if (lane < (int)(4 - s))
+        out[D + lane] = (uint8_t)(src[0] >> (8 * lane));
+    else if (lane >= 4 && lane < (int)(4 + s))
+        out[D - s + 4ull * n + (lane - 4)] = (uint8_t)(src[n - 1] >> (8 * (4 - s + (lane - 4))));
+}
+
+// n words from byte address in + D (any alignment) to dst (aligned).  Reads the aligned word
+// that holds the last byte, i.e. at most 3 bytes past the array (the buffer is padded).
+__device__ __forceinline__ void get_words_at_byte(const uint8_t *in, unsigned long long D, uint32_t *dst, uint32_t n)
+{
+    const int lane = lane_id();
+    const uint32_t s = (uint32_t)(D & 3);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (D - s));
+    for (uint32_t t = lane; t < n; t += 32)
+        dst[t] = s ? __funnelshift_r(src[t], src[t + 1], 8 * s) : src[t];
+}
+
+// Encoder output straight into the container: k_encode_gather with byte-packed destinations
+// and the headers written in place.  One warp per emitted subframe; `sub_base` is the global
+// index of this chunk's first subframe.
+__global__ void __launch_bounds__(256) k_encode_gather_container(EncodeParams p, uint8_t *container,
+                                                                 unsigned long long sub_base)
+{
+    const uint32_t sub = blockIdx.x * 8 + warp_id();
+    const uint32_t n_sub = p.n_frames * p.channels;
+    if (sub >= n_sub || *reinterpret_cast<volatile int32_t *>(p.status) != 0)
+        return;
+    const int lane = lane_id();
+    const Emit e = choose_unit(p.units, p.channels, sub);
+    const selab200_subframe_desc d = p.descs[sub];
+    const uint32_t *slot = p.slots + (size_t)e.unit * kSlotWords;
+    const unsigned long long g = sub_base + sub;
+    const unsigned long long at = container_subframe_byte(g, p.channels, d.refl_offset);
+    if (g % p.channels == 0 && lane >= 12 && lane < 16) {
+        const uint32_t sync = 0xAA55FF00u;
+        container[at - 4 + (lane - 12)] = (uint8_t)(sync >> (8 * (lane - 12)));
+    }
+    const unsigned long long at2 = at + 7 + 4ull * d.refl_words;
+    if (lane < 12) {
+        uint8_t v;
+        switch (lane) {
+        case 0: v = d.channel; break;
+        case 1: v = d.subframe_type; break;
+        case 2: v = d.parent_channel; break;
+        case 3: v = d.refl_rice_param; break;
+        case 4: v = (uint8_t)d.refl_words; break;
+        case 5: v = (uint8_t)(d.refl_words >> 8); break;
+        case 6: v = d.lpc_order; break;
+        case 7: v = d.res_rice_param; break;
+        case 8: v = (uint8_t)d.res_words; break;
+        case 9: v = (uint8_t)(d.res_words >> 8); break;
+        case 10: v = (uint8_t)d.samples; break;
+        default: v = (uint8_t)(d.samples >> 8); break;
+        }
+        container[lane < 7 ? at + lane : at2 + (lane - 7)] = v;
+    }
+    put_words_at_byte(container, at + 7, slot, d.refl_words);
+    put_words_at_byte(container, at2 + 5, slot + kSlotReflWords, d.res_words);
+}
+
+// Decoder input straight from the container: realign the word arrays of each subframe into the
+// (16-byte aligned) arena the Rice decoder reads.  descs[] come from the host's header walk and
+// carry arena offsets in file order.  One warp per subframe.
+__global__ void __launch_bounds__(256) k_container_unpack(const uint8_t *container, const selab200_subframe_desc *descs,
+                                                          uint32_t n_sub, uint32_t channels, unsigned long long sub_base,
+                                                          uint32_t *arena)
+{
+    const uint32_t sub = blockIdx.x * 8 + warp_id();
+    if (sub >= n_sub)
+        return;
+    const selab200_subframe_desc d = descs[sub];
+    const unsigned long long at = container_subframe_byte(sub_base + sub, channels, d.refl_offset);
+    get_words_at_byte(container, at + 7, arena + d.refl_offset, d.refl_words);
+    get_words_at_byte(container, at + 7 + 4ull * d.refl_words + 5, arena + d.res_offset, d.res_words);
+}
+
 // ------------------------------------------------------------------ decode --
 
 __device__ __forceinline__ bool desc_ok(const selab200_subframe_desc &d, uint32_t channels,

@@ -108,6 +108,10 @@ class Encoder {
 public:
     explicit Encoder(std::ifstream &ifStream) : ifStream(ifStream) {}
     file::SelaFile process();
+    // Not in the reference: process() + SelaFile::writeToFile() in one step, byte-identical output.
+    // The WAV data chunk goes to the device as it lies in the file and the .sela byte stream comes
+    // back ready to write (selab200_encode_container): no per-frame value structs on the host.
+    void processTo(std::ofstream &outputFile);
 };
 class Decoder {
     void readFrames();
@@ -118,6 +122,9 @@ class Decoder {
 public:
     explicit Decoder(std::ifstream &ifStream) : ifStream(ifStream) {}
     file::WavFile process();
+    // Not in the reference: process() + WavFile::writeToFile() in one step, byte-identical output
+    // (selab200_container_open / _decode: the .sela bytes go to the device as they lie in the file).
+    void processTo(std::ofstream &outputFile);
 };
 class Player {
 public:

@@ -4,8 +4,13 @@
 // sample is analysed, filtered and coded on the GPU through include/sela_b200.h.
 // Device errors become `throw data::Exception(...)` (src/include/data/exception.hpp:7-14).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
+#include <thread>
 
 #include "sela_api.hpp"
 #include "../../../include/sela_b200.h"
@@ -129,6 +134,160 @@ template <typename T>
 void put(std::ofstream &out, const T &v)
 {
     out.write(reinterpret_cast<const char *>(&v), sizeof v);
+}
+
+// Whole file into an uninitialised heap buffer (no value-initialisation pass over 100 MB).
+struct RawFile {
+    std::unique_ptr<char[]> data;
+    size_t size = 0;
+    const uint8_t *bytes() const { return reinterpret_cast<const uint8_t *>(data.get()); }
+};
+RawFile slurp_raw(std::ifstream &in)
+{
+    RawFile f;
+    in.seekg(0, std::ios::end);
+    const std::streamoff size = in.tellg();
+    f.size = size > 0 ? (size_t)size : 0;
+    f.data.reset(new char[f.size + 1]);
+    in.seekg(0, std::ios::beg);
+    if (f.size)
+        in.read(f.data.get(), (std::streamsize)f.size);
+    return f;
+}
+
+// RIFF walk of file::WavFile::readFromFile (src/file/wav_file.cpp:39-179) without the copies:
+// same acceptance rules, same messages, same order of checks.
+struct WavSpan {
+    std::string id;
+    uint32_t size;
+    size_t body;
+};
+struct WavLayout {
+    uint32_t chunkSize = 0;
+    data::WavFormatSubChunk fmt; // scalar fields only; subChunkData left empty
+    size_t fmtIndex = 0, dataIndex = 0;
+    std::vector<WavSpan> spans;  // every sub-chunk in file order
+};
+struct ByteView {
+    const char *b;
+    uint32_t u8(size_t o) const { return (uint8_t)b[o]; }
+    uint32_t u16(size_t o) const { return u8(o) | (u8(o + 1) << 8); }
+    uint32_t u32(size_t o) const { return u16(o) | (u16(o + 2) << 16); }
+    std::string tag(size_t o) const { return std::string(b + o, b + o + 4); }
+};
+WavLayout scan_wav(const char *contents, size_t n)
+{
+    const ByteView rd{contents};
+    WavLayout w;
+    if (n < 44)
+        raise("File is too small, probably not a wav file.");
+    if (rd.tag(0) != "RIFF")
+        raise("chunkId is not RIFF, probably not a wav file.");
+    w.chunkSize = rd.u32(4);
+    if ((size_t)w.chunkSize > n)
+        raise("chunkSize exceeds file size, probably a corrupted file");
+    if (rd.tag(8) != "WAVE")
+        raise("format is not WAVE, probably not a wav file.");
+    bool haveFmt = false, haveData = false;
+    size_t at = 12;
+    while (at < n) {
+        if (at + 8 > n)
+            raise("truncated sub-chunk header, probably a corrupted file");
+        WavSpan span{rd.tag(at), rd.u32(at + 4), at + 8};
+        if (span.body + span.size > n)
+            raise("sub-chunk exceeds file size, probably a corrupted file");
+        if (span.id == "fmt ") {
+            if (span.size < 16)
+                raise("fmt subChunk is too small");
+            data::WavFormatSubChunk &fmt = w.fmt;
+            fmt.subChunkId = span.id;
+            fmt.subChunkSize = span.size;
+            fmt.audioFormat = (int16_t)rd.u16(span.body);
+            fmt.numChannels = (uint16_t)rd.u16(span.body + 2);
+            fmt.sampleRate = rd.u32(span.body + 4);
+            fmt.byteRate = rd.u32(span.body + 8);
+            fmt.blockAlign = (uint16_t)rd.u16(span.body + 12);
+            fmt.bitsPerSample = (uint16_t)rd.u16(span.body + 14);
+            if (fmt.bitsPerSample != 16)
+                raise("Only 16bits per sample wav is supported.");
+            w.fmtIndex = w.spans.size();
+            haveFmt = true;
+        } else if (span.id == "data") {
+            if (!haveFmt)
+                raise("Probably corrupt wav, data subChunk present without fmt subChunk.");
+            w.dataIndex = w.spans.size();
+            haveData = true;
+        }
+        w.spans.push_back(span);
+        at = span.body + span.size;
+    }
+    if (!haveFmt)
+        raise("fmt subChunk is missing from file");
+    if (!haveData)
+        raise("data subChunk is missing from file");
+    return w;
+}
+
+// SELA_B200_TIMING=1: phase wall times of the file-level drivers on stderr.
+struct Phase {
+    const char *name;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Phase(const char *n) : name(n) {}
+    ~Phase()
+    {
+        static const bool on = std::getenv("SELA_B200_TIMING") != nullptr;
+        if (on)
+            std::fprintf(stderr, "[sela_b200] %-22s %8.2f ms\n", name,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
+// Device bring-up (CUDA context creation, a few hundred ms) on a helper thread while the caller
+// reads its input file; join() rethrows what ensure_device() threw.
+struct DeviceWarmup {
+    std::exception_ptr error;
+    std::thread worker;
+    DeviceWarmup()
+        : worker([this] {
+              try {
+                  Phase p("device init");
+                  ensure_device();
+              } catch (...) {
+                  error = std::current_exception();
+              }
+          })
+    {
+    }
+    void join()
+    {
+        if (worker.joinable())
+            worker.join();
+        if (error)
+            std::rethrow_exception(error);
+    }
+    ~DeviceWarmup()
+    {
+        if (worker.joinable())
+            worker.join();
+    }
+};
+
+void write_wav_header(std::ofstream &outputFile, const data::WavChunk &wavChunk)
+{
+    const data::WavFormatSubChunk &fmt = wavChunk.formatSubChunk;
+    outputFile << wavChunk.chunkId;
+    put(outputFile, wavChunk.chunkSize);
+    outputFile << wavChunk.format;
+    outputFile << fmt.subChunkId;
+    put(outputFile, fmt.subChunkSize);
+    put(outputFile, fmt.audioFormat);
+    put(outputFile, fmt.numChannels);
+    put(outputFile, fmt.sampleRate);
+    put(outputFile, fmt.byteRate);
+    put(outputFile, fmt.blockAlign);
+    put(outputFile, fmt.bitsPerSample);
+    outputFile << wavChunk.dataSubChunk.subChunkId;
+    put(outputFile, wavChunk.dataSubChunk.subChunkSize);
 }
 
 } // namespace
@@ -304,73 +463,47 @@ WavFile::WavFile(uint32_t sampleRate, uint16_t bitsPerSample, uint16_t numChanne
 }
 
 // file::WavFile::readFromFile (src/file/wav_file.cpp:39-179): same acceptance rules and messages
+// (scan_wav), then the reference's value structs filled from the spans it found.
 void WavFile::readFromFile(std::ifstream &inputFile)
 {
     const std::vector<char> contents = slurp(inputFile);
-    const Bytes rd{contents};
-    if (contents.size() < 44)
-        raise("File is too small, probably not a wav file.");
-    wavChunk.chunkId = rd.tag(0);
-    if (wavChunk.chunkId != "RIFF")
-        raise("chunkId is not RIFF, probably not a wav file.");
-    wavChunk.chunkSize = rd.u32(4);
-    if ((size_t)wavChunk.chunkSize > contents.size())
-        raise("chunkSize exceeds file size, probably a corrupted file");
-    wavChunk.format = rd.tag(8);
-    if (wavChunk.format != "WAVE")
-        raise("format is not WAVE, probably not a wav file.");
-
-    bool haveFmt = false, haveData = false;
-    size_t at = 12;
-    while (at < contents.size()) {
-        if (at + 8 > contents.size())
-            raise("truncated sub-chunk header, probably a corrupted file");
-        const std::string id = rd.tag(at);
-        const uint32_t size = rd.u32(at + 4);
-        const size_t body = at + 8;
-        if (body + size > contents.size())
-            raise("sub-chunk exceeds file size, probably a corrupted file");
-        if (id == "fmt ") {
-            if (size < 16)
-                raise("fmt subChunk is too small");
+    const WavLayout w = scan_wav(contents.data(), contents.size());
+    wavChunk.chunkId = "RIFF";
+    wavChunk.chunkSize = w.chunkSize;
+    wavChunk.format = "WAVE";
+    wavChunk.wavSubChunks.clear();
+    for (size_t i = 0; i < w.spans.size(); i++) {
+        const WavSpan &span = w.spans[i];
+        const auto first = contents.begin() + span.body, last = first + span.size;
+        if (span.id == "fmt ") { // a later fmt chunk replaces an earlier one, as in the reference's loop
             data::WavFormatSubChunk fmt;
-            fmt.subChunkId = id;
-            fmt.subChunkSize = size;
-            fmt.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
-            fmt.audioFormat = (int16_t)rd.u16(body);
-            fmt.numChannels = (uint16_t)rd.u16(body + 2);
-            fmt.sampleRate = rd.u32(body + 4);
-            fmt.byteRate = rd.u32(body + 8);
-            fmt.blockAlign = (uint16_t)rd.u16(body + 12);
-            fmt.bitsPerSample = (uint16_t)rd.u16(body + 14);
-            if (fmt.bitsPerSample != 16)
-                raise("Only 16bits per sample wav is supported.");
+            const ByteView rd{contents.data()};
+            fmt.subChunkId = span.id;
+            fmt.subChunkSize = span.size;
+            fmt.subChunkData.assign(first, last);
+            fmt.audioFormat = (int16_t)rd.u16(span.body);
+            fmt.numChannels = (uint16_t)rd.u16(span.body + 2);
+            fmt.sampleRate = rd.u32(span.body + 4);
+            fmt.byteRate = rd.u32(span.body + 8);
+            fmt.blockAlign = (uint16_t)rd.u16(span.body + 12);
+            fmt.bitsPerSample = (uint16_t)rd.u16(span.body + 14);
             wavChunk.formatSubChunk = fmt;
-            haveFmt = true;
-        } else if (id == "data") {
-            if (!haveFmt)
-                raise("Probably corrupt wav, data subChunk present without fmt subChunk.");
+        } else if (span.id == "data") {
             data::WavDataSubChunk dat;
-            dat.subChunkId = id;
-            dat.subChunkSize = size;
+            dat.subChunkId = span.id;
+            dat.subChunkSize = span.size;
             dat.bitsPerSample = 0; // the reference leaves these two zero as well (wav_file.cpp:84-85,134-135)
             dat.channels = 0;
-            dat.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
+            dat.subChunkData.assign(first, last);
             wavChunk.dataSubChunk = dat;
-            haveData = true;
         } else {
             data::WavSubChunk other;
-            other.subChunkId = id;
-            other.subChunkSize = size;
-            other.subChunkData.assign(contents.begin() + body, contents.begin() + body + size);
+            other.subChunkId = span.id;
+            other.subChunkSize = span.size;
+            other.subChunkData.assign(first, last);
             wavChunk.wavSubChunks.push_back(other);
         }
-        at = body + size;
     }
-    if (!haveFmt)
-        raise("fmt subChunk is missing from file");
-    if (!haveData)
-        raise("data subChunk is missing from file");
     demuxSamples();
 }
 
@@ -401,20 +534,7 @@ void WavFile::demuxSamples()
 // (the reference has a fast path for stereo only; the layout is identical)
 void WavFile::writeToFile(std::ofstream &outputFile)
 {
-    const data::WavFormatSubChunk &fmt = wavChunk.formatSubChunk;
-    outputFile << wavChunk.chunkId;
-    put(outputFile, wavChunk.chunkSize);
-    outputFile << wavChunk.format;
-    outputFile << fmt.subChunkId;
-    put(outputFile, fmt.subChunkSize);
-    put(outputFile, fmt.audioFormat);
-    put(outputFile, fmt.numChannels);
-    put(outputFile, fmt.sampleRate);
-    put(outputFile, fmt.byteRate);
-    put(outputFile, fmt.blockAlign);
-    put(outputFile, fmt.bitsPerSample);
-    outputFile << wavChunk.dataSubChunk.subChunkId;
-    put(outputFile, wavChunk.dataSubChunk.subChunkSize);
+    write_wav_header(outputFile, wavChunk);
     std::vector<int16_t> block;
     for (const data::WavFrame &f : wavChunk.dataSubChunk.wavFrames) {
         const size_t channels = f.samples.size();
@@ -575,7 +695,88 @@ file::SelaFile Encoder::process()
     return file::SelaFile(fmt.sampleRate, fmt.bitsPerSample, (uint8_t)fmt.numChannels, std::move(frames));
 }
 
+// process() + file::SelaFile::writeToFile() without the detour through per-frame value structs:
+// the data chunk is handed to the device where it lies in the file buffer, and what comes back is
+// the .sela byte stream.  Output is byte-identical to the two-step path (tests/test_host_cli.py).
+void Encoder::processTo(std::ofstream &outputFile)
+{
+    DeviceWarmup warmup; // CUDA context creation overlaps the file read
+    RawFile file;
+    {
+        Phase p("read input");
+        file = slurp_raw(ifStream);
+    }
+    const WavLayout w = scan_wav(file.data.get(), file.size);
+    const WavSpan &dat = w.spans[w.dataIndex];
+    const uint32_t channels = w.fmt.numChannels;
+    if (channels == 0)
+        raise("fmt subChunk declares zero channels");
+    // file::WavFile::demuxSamples (src/file/wav_file.cpp:181-220): whole frames only
+    const size_t sampleCount = ((size_t)dat.size * 8) / w.fmt.bitsPerSample;
+    const size_t n_frames = sampleCount / ((size_t)kFrame * channels);
+    warmup.join();
+    if (n_frames > 0 && channels > SELAB200_MAX_CHANNELS)
+        raise("sela_b200: unsupported channel count");
+    if (n_frames > UINT32_MAX)
+        raise("sela_b200: too many frames");
+    if (n_frames == 0) { // header only, as SelaFile::writeToFile does for an empty frame list
+        file::SelaFile(w.fmt.sampleRate, w.fmt.bitsPerSample, (uint8_t)channels, {}).writeToFile(outputFile);
+        return;
+    }
+    const size_t cap = selab200_container_bound((uint32_t)n_frames, channels);
+    std::unique_ptr<uint8_t[]> out(new uint8_t[cap]);
+    size_t used = 0;
+    {
+        Phase p("encode (device)");
+        check(selab200_encode_container(reinterpret_cast<const int16_t *>(file.data.get() + dat.body), (uint32_t)n_frames,
+                                        channels, w.fmt.sampleRate, w.fmt.bitsPerSample, out.get(), cap, &used));
+    }
+    Phase p("write output");
+    outputFile.write(reinterpret_cast<const char *>(out.get()), (std::streamsize)used);
+}
+
 void Decoder::readFrames() { selaFile.readFromFile(ifStream); }
+
+// process() + file::WavFile::writeToFile() in one step: the .sela bytes go to the device as they
+// lie in the file (the library walks the frame headers while the upload runs), interleaved int16
+// PCM -- the WAV data chunk -- comes back.
+void Decoder::processTo(std::ofstream &outputFile)
+{
+    DeviceWarmup warmup;
+    RawFile file;
+    {
+        Phase p("read input");
+        file = slurp_raw(ifStream);
+    }
+    warmup.join();
+    selab200_container *handle = nullptr;
+    selab200_container_info info;
+    {
+        Phase p("open (upload + walk)");
+        if (selab200_container_open(file.bytes(), file.size, &handle, &info) != SELAB200_OK)
+            raise(selab200_last_error()); // the reader's own messages (too small / magic / truncated)
+    }
+    struct Closer {
+        selab200_container *h;
+        ~Closer() { selab200_container_close(h); }
+    } closer{handle};
+    if (info.n_frames > 0 && (info.channels == 0 || info.channels > SELAB200_MAX_CHANNELS))
+        raise("sela_b200: unsupported channel count");
+    const size_t n_samples = (size_t)info.n_frames * info.channels * kFrame;
+    std::unique_ptr<int16_t[]> pcm(new int16_t[n_samples + 1]);
+    {
+        Phase p("decode (device)");
+        check(selab200_container_decode(handle, pcm.get()));
+    }
+    Phase p("write output");
+    // header exactly as file::WavFile::WavFile computes it from the decoded frames (wav_file.cpp:7-37)
+    file::WavFile shell(info.sample_rate, info.bits_per_sample, info.channels, {});
+    const size_t payload = n_samples * (info.bits_per_sample / 8);
+    shell.wavChunk.chunkSize = (uint32_t)(payload + 36);
+    shell.wavChunk.dataSubChunk.subChunkSize = (uint32_t)payload;
+    write_wav_header(outputFile, shell.wavChunk);
+    outputFile.write(reinterpret_cast<const char *>(pcm.get()), (std::streamsize)(n_samples * 2));
+}
 
 // sela::Decoder::processFrames (src/sela/decoder.cpp:41-92)
 void Decoder::processFrames(std::vector<data::WavFrame> &decodedWavFrames)

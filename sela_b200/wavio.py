@@ -26,3 +26,24 @@ def read_wav_pcm(path):
     channels, rate = struct.unpack("<H", raw[22:24])[0], struct.unpack("<I", raw[24:28])[0]
     n = struct.unpack("<I", raw[40:44])[0]
     return rate, channels, np.frombuffer(raw[44:44 + n], dtype="<i2").reshape(-1, channels)
+
+
+SELA_SYNC = b"\x00\xff\x55\xaa"  # 0xAA55FF00 little endian (src/include/data/sela_frame.hpp)
+
+
+def pack_container(descs, words, sample_rate, channels, bits_per_sample=16):
+    """(descs, words) of whole frames -> the bytes file::SelaFile::writeToFile emits
+    (src/file/sela_file.cpp:105-137).  Plain byte shuffling for tests and tools."""
+    words = np.ascontiguousarray(words, dtype="<u4")
+    n_frames = len(descs) // channels
+    out = [b"SeLa" + struct.pack("<IHBI", sample_rate, bits_per_sample, channels, n_frames)]
+    for f in range(n_frames):
+        out.append(SELA_SYNC)
+        for d in descs[f * channels:(f + 1) * channels]:
+            a, b = int(d["refl_offset"]), int(d["res_offset"])
+            out.append(struct.pack("<BBBBHB", d["channel"], d["subframe_type"], d["parent_channel"],
+                                   d["refl_rice_param"], d["refl_words"], d["lpc_order"]))
+            out.append(words[a:a + int(d["refl_words"])].tobytes())
+            out.append(struct.pack("<BHH", d["res_rice_param"], d["res_words"], d["samples"]))
+            out.append(words[b:b + int(d["res_words"])].tobytes())
+    return b"".join(out)

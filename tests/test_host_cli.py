@@ -17,8 +17,10 @@ BIN = ROOT / "sela_b200" / "host" / "bin"
 REF_CLI = ROOT / "oracle" / "_ref" / "sela_ref_cli"
 
 
-def _run(*cmd, ok=True):
-    p = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=600)
+def _run(*cmd, ok=True, env=None):
+    import os
+    p = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **env) if env else None)
     if ok:
         assert p.returncode == 0, (cmd, p.stdout[-400:], p.stderr[-400:])
     return p
@@ -87,17 +89,22 @@ def test_reference_unit_tests_on_mirror_classes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("binary", ["sela", "sela_refmain"])
+@pytest.mark.parametrize("binary", ["sela", "sela-classic", "sela_refmain"])
 def test_cli_byte_parity_with_reference_cli(tmp_path, binary):
+    """`sela`: the fused file-to-file drivers (Encoder/Decoder::processTo over the container entry
+    points); `sela-classic`: the same binary on the reference's two-step call sequence;
+    `sela_refmain`: the reference's own main.cpp compiled unchanged over the mirror classes."""
     _ensure_built()
+    env = {"SELA_B200_CLASSIC": "1"} if binary == "sela-classic" else None
+    binary = binary.split("-")[0]
     if not (BIN / binary).exists():
         pytest.skip("%s not built (needs the reference tree at build time)" % binary)
     have_ref = REF_CLI.exists()
     for name, wav in _cases(tmp_path).items():
         ours_sela, ours_wav = tmp_path / (name + ".sela"), tmp_path / (name + ".out.wav")
-        p = _run(BIN / binary, "-e", wav, ours_sela)
+        p = _run(BIN / binary, "-e", wav, ours_sela, env=env)
         assert "Encoding: " in p.stdout
-        _run(BIN / binary, "-d", ours_sela, ours_wav)
+        _run(BIN / binary, "-d", ours_sela, ours_wav, env=env)
         if have_ref:
             ref_sela, ref_wav = tmp_path / (name + ".ref.sela"), tmp_path / (name + ".ref.wav")
             _run(REF_CLI, "-e", wav, ref_sela)
@@ -120,3 +127,23 @@ def test_cli_error_convention(tmp_path):
     assert p.returncode == 1 and "chunkId is not RIFF" in p.stderr
     p = _run(BIN / "sela", ok=True)
     assert "Usage:" in p.stdout
+    # decode side: the reader's messages, on both call sequences
+    wavio.write_wav(tmp_path / "a.wav", synth.sine_noise(8000, 1, n_frames=3, seed=1), 8000)
+    _run(BIN / "sela", "-e", tmp_path / "a.wav", tmp_path / "a.sela")
+    blob = (tmp_path / "a.sela").read_bytes()
+    (tmp_path / "cut.sela").write_bytes(blob[:-9])
+    (tmp_path / "magic.sela").write_bytes(b"SeLb" + blob[4:])
+    (tmp_path / "tiny.sela").write_bytes(blob[:10])
+    for env in (None, {"SELA_B200_CLASSIC": "1"}):
+        for name, msg in (("cut", "sela file is truncated"), ("magic", "Magic number is incorrect"),
+                          ("tiny", "File is too small, probably not a sela file.")):
+            p = _run(BIN / "sela", "-d", tmp_path / (name + ".sela"), tmp_path / "o.wav", ok=False, env=env)
+            assert p.returncode == 1 and msg in p.stderr, (name, env, p.stderr)
+    # an empty WAV (no whole frame) encodes to the bare header and decodes to a bare WAV header
+    wavio.write_wav(tmp_path / "short.wav", np.zeros((100, 2), np.int16), 44100)
+    outs = []
+    for env in (None, {"SELA_B200_CLASSIC": "1"}):
+        _run(BIN / "sela", "-e", tmp_path / "short.wav", tmp_path / "short.sela", env=env)
+        _run(BIN / "sela", "-d", tmp_path / "short.sela", tmp_path / "short.out.wav", env=env)
+        outs.append(((tmp_path / "short.sela").read_bytes(), (tmp_path / "short.out.wav").read_bytes()))
+    assert outs[0] == outs[1] and len(outs[0][0]) == 15 and len(outs[0][1]) == 44

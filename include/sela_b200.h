@@ -181,6 +181,14 @@ int selab200_encode_container(const int16_t *pcm, uint32_t n_frames, uint32_t ch
  * carry the message the host mirror throws for the same file: too small, bad magic, truncated. */
 int selab200_container_info_get(const uint8_t *container, size_t n_bytes, selab200_container_info *info);
 
+/* Same walk, also returning where each frame starts: offsets[i] = byte position of frame i's sync
+ * word, offsets[n_frames] = one past the last frame.  Frames are independent, so a byte range
+ * [offsets[a], offsets[b]) behind a 15-byte header that says b-a frames is itself a container --
+ * which is how a file is cut into per-GPU blocks (sela_b200/distributed.py).  Host only.
+ * SELAB200_ERR_CAPACITY if capacity < n_frames + 1 (info is filled in either way). */
+int selab200_container_frame_offsets(const uint8_t *container, size_t n_bytes, uint64_t *offsets,
+                                     size_t capacity, selab200_container_info *info);
+
 /* Complete .sela byte stream -> interleaved int16 PCM (the WAV data chunk):
  * file::SelaFile::readFromFile + sela::Decoder::processFrames.  open: parses the header, starts
  * the upload and walks the frame headers on the host meanwhile (the walk is a pointer chase

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "selab200_container_bound": (_SZ, [_U32, _U32]),
     "selab200_encode_container": (_I, [_V, _U32, _U32, _U32, C.c_uint16, _V, _SZ, _V]),
     "selab200_container_info_get": (_I, [_V, _SZ, _V]),
+    "selab200_container_frame_offsets": (_I, [_V, _SZ, _V, _SZ, _V]),
     "selab200_container_open": (_I, [_V, _SZ, _V, _V]),
     "selab200_container_decode": (_I, [_V, _V]),
     "selab200_container_close": (None, [_V]),

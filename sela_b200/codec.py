@@ -143,6 +143,18 @@ def container_info(container):
     return {k: int(info[0][k]) for k in INFO_DTYPE.names if k != "reserved"}
 
 
+def container_frame_offsets(container):
+    """(info dict, uint64 array of n_frames+1 byte offsets: frame starts and the end) -- host only."""
+    buf = _c(np.frombuffer(container, np.uint8) if isinstance(container, (bytes, bytearray)) else container, np.uint8)
+    info = np.zeros(1, INFO_DTYPE)
+    L = lib()
+    check(L.selab200_container_info_get(buf.ctypes.data, buf.size, info.ctypes.data))
+    offsets = np.zeros(int(info[0]["n_frames"]) + 1, np.uint64)
+    check(L.selab200_container_frame_offsets(buf.ctypes.data, buf.size, offsets.ctypes.data, offsets.size,
+                                             info.ctypes.data))
+    return {k: int(info[0][k]) for k in INFO_DTYPE.names if k != "reserved"}, offsets
+
+
 def decode_container(container, device=0):
     """.sela byte stream -> (info dict, int16 interleaved PCM of info['n_frames'] frames)."""
     init(device)

@@ -707,7 +707,8 @@ namespace {
 // header, then hops from frame to frame.  With `descs` it also emits one descriptor per subframe,
 // arena offsets assigned in file order.  Messages match the host mirror's reader.
 int walk_container(const uint8_t *b, size_t n, selab200_container_info *info,
-                   std::vector<selab200_subframe_desc> *descs)
+                   std::vector<selab200_subframe_desc> *descs, uint64_t *frame_bytes = nullptr,
+                   size_t frame_capacity = 0)
 {
     memset(info, 0, sizeof *info);
     if (n < 15)
@@ -727,6 +728,8 @@ int walk_container(const uint8_t *b, size_t n, selab200_container_info *info,
     for (; f < info->header_frames; f++) {
         if (at + 4 > n || u32(at) != 0xAA55FF00u)
             break;
+        if (frame_bytes && f < frame_capacity)
+            frame_bytes[f] = at;
         at += 4;
         for (uint32_t c = 0; c < channels; c++) {
             if (at + 7 > n)
@@ -761,6 +764,8 @@ int walk_container(const uint8_t *b, size_t n, selab200_container_info *info,
     info->n_frames = f;
     info->n_words = words;
     info->n_bytes_used = at;
+    if (frame_bytes && f < frame_capacity)
+        frame_bytes[f] = at;
     return 0;
 }
 
@@ -773,6 +778,18 @@ int selab200_container_info_get(const uint8_t *container, size_t n_bytes, selab2
     if (!container || !info)
         return fail(SELAB200_ERR_ARGUMENT, "null pointer");
     return walk_container(container, n_bytes, info, nullptr);
+}
+
+int selab200_container_frame_offsets(const uint8_t *container, size_t n_bytes, uint64_t *offsets, size_t capacity,
+                                     selab200_container_info *info)
+{
+    if (!container || !offsets || !info)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (int rc = walk_container(container, n_bytes, info, nullptr, offsets, capacity))
+        return rc;
+    if ((size_t)info->n_frames + 1 > capacity)
+        return fail(SELAB200_ERR_CAPACITY, "offset table too small: %zu entries, need %u", capacity, info->n_frames + 1);
+    return 0;
 }
 
 void selab200_container_close(selab200_container *h)

@@ -178,3 +178,127 @@ def decode_sharded(descs, words, n_frames, channels, decode_fn, root=0):
         a, b = frame_block(n_frames, r, world)
         out[a * FRAME * channels:b * FRAME * channels] = t.cpu().numpy().view(np.int16)
     return out
+
+
+def _pwrite_all(path, data, offset):
+    """pwrite until everything is out (a single call may stop short on large buffers)."""
+    import os
+    view = memoryview(data)
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        done = 0
+        while done < len(view):
+            done += os.pwrite(fd, view[done:], offset + done)
+    finally:
+        os.close(fd)
+
+
+# ---------------------------------------------------------------- whole files --
+#
+# When every rank can open the files (one box, BASELINE config 4), nothing has to travel between
+# GPUs at all: WAV frames sit at fixed byte positions, so each rank reads its own block of the input;
+# the only thing ranks must agree on is WHERE in the output each block lands, i.e. one all_gather of
+# body lengths (encode) or one broadcast of frame byte offsets from the rank that walked the headers
+# (decode).  Every subframe of a .sela stream starts at a byte position = 3 (mod 4) whatever precedes
+# it (15 + 4(f+1) + 12g + 4W), so a block coded as a stand-alone container is, minus its 15-byte
+# header, exactly the byte range it occupies in the whole file.
+
+_SELA_HEADER = 15
+
+
+def _wav_layout(path):
+    """(sample_rate, channels, bits, data_offset, data_bytes) of a RIFF/WAVE file (any chunk order)."""
+    import struct
+    with open(path, "rb") as f:
+        head = f.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            raise ValueError("%s: not a RIFF/WAVE file" % path)
+        fmt = None
+        while True:
+            hdr = f.read(8)
+            if len(hdr) < 8:
+                raise ValueError("%s: no data chunk" % path)
+            cid, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
+            if cid == b"fmt ":
+                body = f.read(size)
+                _, channels, rate, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+                fmt = (rate, channels, bits)
+            elif cid == b"data":
+                if fmt is None:
+                    raise ValueError("%s: data chunk before fmt chunk" % path)
+                return fmt + (f.tell(), size)
+            else:
+                f.seek(size, 1)
+
+
+def encode_file_sharded(wav_path, sela_path, container_fn):
+    """Every rank encodes its block of `wav_path`'s frames with `container_fn(pcm, channels, rate) ->
+    bytes of a stand-alone .sela container` and writes it in place into `sela_path`.  The result is
+    byte-identical to a single-process encode.  Returns (n_frames, total_bytes)."""
+    import struct
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rate, channels, bits, data_off, data_bytes = _wav_layout(wav_path)
+    if bits != 16:
+        raise ValueError("Only 16bits per sample wav is supported.")
+    stride = FRAME * channels * 2
+    n_frames = data_bytes // stride                       # whole frames only (src/file/wav_file.cpp:184)
+    lo, hi = frame_block(n_frames, rank, world)
+    pcm = np.fromfile(wav_path, dtype="<i2", offset=data_off + lo * stride, count=(hi - lo) * FRAME * channels)
+    body = bytes(container_fn(pcm, channels, rate))[_SELA_HEADER:] if hi > lo else b""
+    mine = torch.tensor([len(body)], dtype=torch.int64, device=_dev())
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine)
+    sizes = [int(t.item()) for t in sizes]
+    total = _SELA_HEADER + sum(sizes)
+    if rank == 0:
+        with open(sela_path, "wb") as f:
+            f.write(b"SeLa" + struct.pack("<IHBI", rate, bits, channels, n_frames))
+            f.truncate(total)
+    dist.barrier()
+    if body:
+        _pwrite_all(sela_path, body, _SELA_HEADER + sum(sizes[:rank]))
+    dist.barrier()
+    return n_frames, total
+
+
+def decode_file_sharded(sela_path, wav_path, frame_offsets_fn, decode_fn):
+    """Rank 0 walks the frame headers (`frame_offsets_fn(bytes) -> (info, offsets)`, host only) and
+    broadcasts the block boundaries; every rank reads its byte range, decodes it as a stand-alone
+    container (`decode_fn(bytes) -> int16 PCM`) and writes its slice of the WAV data chunk.
+    Returns n_frames."""
+    import struct
+    rank, world = dist.get_rank(), dist.get_world_size()
+    meta = torch.zeros(4 + world + 1, dtype=torch.int64, device=_dev())
+    if rank == 0:
+        blob = np.memmap(sela_path, dtype=np.uint8, mode="r")
+        info, offsets = frame_offsets_fn(blob)
+        n_frames = info["n_frames"]
+        cuts = [int(offsets[frame_block(n_frames, r, world)[0]]) for r in range(world)] + [int(offsets[n_frames])]
+        meta[:] = torch.tensor([n_frames, info["channels"], info["sample_rate"], info["bits_per_sample"]] + cuts)
+        del blob
+    dist.broadcast(meta, 0)
+    meta = meta.cpu().tolist()
+    n_frames, channels, rate, bits = meta[:4]
+    cuts = meta[4:]
+    lo, hi = frame_block(n_frames, rank, world)
+    stride = FRAME * channels * 2
+    payload = n_frames * channels * FRAME * (bits // 8)
+    if rank == 0:
+        with open(wav_path, "wb") as f:  # header of file::WavFile::WavFile (src/file/wav_file.cpp:7-37)
+            f.write(b"RIFF" + struct.pack("<I", (payload + 36) & 0xffffffff) + b"WAVEfmt " +
+                    struct.pack("<IHHIIHH", 16, 1, channels, rate, (rate * channels * bits) // 8 & 0xffffffff,
+                                (channels * bits) // 8, bits) +
+                    b"data" + struct.pack("<I", payload & 0xffffffff))
+            f.truncate(44 + n_frames * stride)
+    dist.barrier()
+    if hi > lo:
+        with open(sela_path, "rb") as f:
+            f.seek(cuts[rank])
+            body = f.read(cuts[rank + 1] - cuts[rank])
+        block = b"SeLa" + struct.pack("<IHBI", rate, bits, channels, hi - lo) + body
+        pcm = np.ascontiguousarray(decode_fn(block), dtype="<i2")
+        if pcm.size != (hi - lo) * FRAME * channels:
+            raise ValueError("block decoded to %d samples, expected %d" % (pcm.size, (hi - lo) * FRAME * channels))
+        _pwrite_all(wav_path, pcm.view(np.uint8).reshape(-1), 44 + lo * stride)
+    dist.barrier()
+    return n_frames

@@ -43,6 +43,12 @@ def cases():
     out["edge_stereo"] = np.concatenate(
         [np.stack([fam[n], fam[names[(i * 5 + 2) % len(names)]]], axis=1) for i, n in enumerate(names)]).astype(np.int16)
     out["three"] = synth.sine_noise(32000, 3, n_frames=2, seed=9)
+    # Two frames of the config-4-shaped 10-minute file (48 kHz, 8 channels, seed 2) on which the REFERENCE is
+    # not lossless: its decoder departs from the source at sample 1 of one channel (frame 8975 channel 1,
+    # frame 13577 channel 4; encoder and decoder round the prediction differently when the Q35 sum lands
+    # exactly on a half).  The decoded_* array pins what the reference decoder returns.
+    big = synth.sine_noise(48000, 8, 600, seed=2)
+    out["oct_reference_lossy"] = np.concatenate([big[8975 * 2048:8976 * 2048], big[13577 * 2048:13578 * 2048]])
     return out
 
 

@@ -132,7 +132,7 @@ def encode_container(pcm, channels, sample_rate, bits_per_sample=16, capacity=No
     used = C.c_size_t(0)
     check(L.selab200_encode_container(pcm.ctypes.data, n_frames, channels, sample_rate, bits_per_sample,
                                       out.ctypes.data, cap, C.addressof(used)))
-    return out[:used.value].copy()
+    return out[:used.value]
 
 
 def container_info(container):

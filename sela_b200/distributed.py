@@ -244,7 +244,8 @@ def encode_file_sharded(wav_path, sela_path, container_fn):
     n_frames = data_bytes // stride                       # whole frames only (src/file/wav_file.cpp:184)
     lo, hi = frame_block(n_frames, rank, world)
     pcm = np.fromfile(wav_path, dtype="<i2", offset=data_off + lo * stride, count=(hi - lo) * FRAME * channels)
-    body = bytes(container_fn(pcm, channels, rate))[_SELA_HEADER:] if hi > lo else b""
+    body = memoryview(np.ascontiguousarray(np.frombuffer(container_fn(pcm, channels, rate), np.uint8)))[_SELA_HEADER:] \
+        if hi > lo else b""
     mine = torch.tensor([len(body)], dtype=torch.int64, device=_dev())
     sizes = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(sizes, mine)

@@ -126,6 +126,11 @@ public:
     // (selab200_container_open / _decode: the .sela bytes go to the device as they lie in the file).
     void processTo(std::ofstream &outputFile);
 };
+// Not in the reference.  On: the processTo() drivers keep page-locked staging buffers per host thread
+// and reuse them from file to file (a process that codes many files, e.g. `sela -E`); off (default):
+// plain memory, released when the call returns.
+void setBatchMode(bool on);
+
 class Player {
 public:
     void play(const file::WavFile &wavFile); // always throws: playback (libao) is out of scope

@@ -9,7 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "sela_api.hpp"
@@ -32,7 +34,9 @@ void check(int status)
 
 void ensure_device()
 {
+    static std::mutex m;
     static bool ready = false;
+    std::lock_guard<std::mutex> lock(m);
     if (ready)
         return;
     const char *env = std::getenv("SELAB200_DEVICE");
@@ -136,22 +140,70 @@ void put(std::ofstream &out, const T &v)
     out.write(reinterpret_cast<const char *>(&v), sizeof v);
 }
 
-// Whole file into an uninitialised heap buffer (no value-initialisation pass over 100 MB).
-struct RawFile {
-    std::unique_ptr<char[]> data;
-    size_t size = 0;
-    const uint8_t *bytes() const { return reinterpret_cast<const uint8_t *>(data.get()); }
+// Staging memory of the file-to-file drivers, one pair (input, output) per host thread.
+// One-shot use (the CLI coding one file): plain heap memory, released when the call returns --
+// page-locking 200 MB costs more than the pageable copies it would save.  Batch mode
+// (sela::setBatchMode, many files per process): page-locked, kept and reused from file to file, so
+// that uploads and downloads run at full PCIe speed and overlap the kernels.
+std::atomic<bool> g_batch_mode{false};
+
+struct HostBuffer {
+    char *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    void release()
+    {
+        if (p && pinned)
+            selab200_host_free(p);
+        else
+            delete[] p;
+        p = nullptr;
+        cap = 0;
+    }
+    // uninitialised memory: no value-initialisation pass over 100 MB
+    char *ensure(size_t n)
+    {
+        const bool want_pinned = g_batch_mode.load();
+        if (p && n <= cap && pinned == want_pinned)
+            return p;
+        release();
+        const size_t want = want_pinned ? n + n / 4 + 4096 : n + 1;
+        pinned = want_pinned;
+        p = pinned ? static_cast<char *>(selab200_host_alloc(want)) : new char[want];
+        if (!p)
+            raise("sela_b200: host staging allocation failed");
+        cap = want;
+        return p;
+    }
+    ~HostBuffer() { release(); }
 };
+thread_local HostBuffer t_input, t_output;
+struct StagingScope { // one-shot use gives the memory back; batch mode keeps it for the next file
+    ~StagingScope()
+    {
+        if (!g_batch_mode.load()) {
+            t_input.release();
+            t_output.release();
+        }
+    }
+};
+
+struct RawFile {
+    char *data = nullptr;
+    size_t size = 0;
+    const uint8_t *bytes() const { return reinterpret_cast<const uint8_t *>(data); }
+};
+// Whole file into this thread's input staging buffer.
 RawFile slurp_raw(std::ifstream &in)
 {
     RawFile f;
     in.seekg(0, std::ios::end);
     const std::streamoff size = in.tellg();
     f.size = size > 0 ? (size_t)size : 0;
-    f.data.reset(new char[f.size + 1]);
+    f.data = t_input.ensure(f.size + 1);
     in.seekg(0, std::ios::beg);
     if (f.size)
-        in.read(f.data.get(), (std::streamsize)f.size);
+        in.read(f.data, (std::streamsize)f.size);
     return f;
 }
 
@@ -700,13 +752,16 @@ file::SelaFile Encoder::process()
 // the .sela byte stream.  Output is byte-identical to the two-step path (tests/test_host_cli.py).
 void Encoder::processTo(std::ofstream &outputFile)
 {
+    StagingScope staging;
     DeviceWarmup warmup; // CUDA context creation overlaps the file read
+    if (g_batch_mode.load())
+        warmup.join();   // page-locked staging needs the device; it is up after the first file anyway
     RawFile file;
     {
         Phase p("read input");
         file = slurp_raw(ifStream);
     }
-    const WavLayout w = scan_wav(file.data.get(), file.size);
+    const WavLayout w = scan_wav(file.data, file.size);
     const WavSpan &dat = w.spans[w.dataIndex];
     const uint32_t channels = w.fmt.numChannels;
     if (channels == 0)
@@ -724,15 +779,15 @@ void Encoder::processTo(std::ofstream &outputFile)
         return;
     }
     const size_t cap = selab200_container_bound((uint32_t)n_frames, channels);
-    std::unique_ptr<uint8_t[]> out(new uint8_t[cap]);
+    uint8_t *out = reinterpret_cast<uint8_t *>(t_output.ensure(cap));
     size_t used = 0;
     {
         Phase p("encode (device)");
-        check(selab200_encode_container(reinterpret_cast<const int16_t *>(file.data.get() + dat.body), (uint32_t)n_frames,
-                                        channels, w.fmt.sampleRate, w.fmt.bitsPerSample, out.get(), cap, &used));
+        check(selab200_encode_container(reinterpret_cast<const int16_t *>(file.data + dat.body), (uint32_t)n_frames,
+                                        channels, w.fmt.sampleRate, w.fmt.bitsPerSample, out, cap, &used));
     }
     Phase p("write output");
-    outputFile.write(reinterpret_cast<const char *>(out.get()), (std::streamsize)used);
+    outputFile.write(reinterpret_cast<const char *>(out), (std::streamsize)used);
 }
 
 void Decoder::readFrames() { selaFile.readFromFile(ifStream); }
@@ -742,7 +797,10 @@ void Decoder::readFrames() { selaFile.readFromFile(ifStream); }
 // PCM -- the WAV data chunk -- comes back.
 void Decoder::processTo(std::ofstream &outputFile)
 {
+    StagingScope staging;
     DeviceWarmup warmup;
+    if (g_batch_mode.load())
+        warmup.join();
     RawFile file;
     {
         Phase p("read input");
@@ -763,10 +821,10 @@ void Decoder::processTo(std::ofstream &outputFile)
     if (info.n_frames > 0 && (info.channels == 0 || info.channels > SELAB200_MAX_CHANNELS))
         raise("sela_b200: unsupported channel count");
     const size_t n_samples = (size_t)info.n_frames * info.channels * kFrame;
-    std::unique_ptr<int16_t[]> pcm(new int16_t[n_samples + 1]);
+    int16_t *pcm = reinterpret_cast<int16_t *>(t_output.ensure((n_samples + 1) * 2));
     {
         Phase p("decode (device)");
-        check(selab200_container_decode(handle, pcm.get()));
+        check(selab200_container_decode(handle, pcm));
     }
     Phase p("write output");
     // header exactly as file::WavFile::WavFile computes it from the decoded frames (wav_file.cpp:7-37)
@@ -775,7 +833,7 @@ void Decoder::processTo(std::ofstream &outputFile)
     shell.wavChunk.chunkSize = (uint32_t)(payload + 36);
     shell.wavChunk.dataSubChunk.subChunkSize = (uint32_t)payload;
     write_wav_header(outputFile, shell.wavChunk);
-    outputFile.write(reinterpret_cast<const char *>(pcm.get()), (std::streamsize)(n_samples * 2));
+    outputFile.write(reinterpret_cast<const char *>(pcm), (std::streamsize)(n_samples * 2));
 }
 
 // sela::Decoder::processFrames (src/sela/decoder.cpp:41-92)
@@ -823,6 +881,8 @@ file::WavFile Decoder::process()
     return file::WavFile(selaFile.selaHeader.sampleRate, selaFile.selaHeader.bitsPerSample,
                          selaFile.selaHeader.channels, std::move(frames));
 }
+
+void setBatchMode(bool on) { g_batch_mode.store(on); }
 
 void Player::play(const file::WavFile &)
 {

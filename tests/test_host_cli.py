@@ -147,3 +147,30 @@ def test_cli_error_convention(tmp_path):
         _run(BIN / "sela", "-d", tmp_path / "short.sela", tmp_path / "short.out.wav", env=env)
         outs.append(((tmp_path / "short.sela").read_bytes(), (tmp_path / "short.out.wav").read_bytes()))
     assert outs[0] == outs[1] and len(outs[0][0]) == 15 and len(outs[0][1]) == 44
+
+
+@pytest.mark.gpu
+def test_cli_batch_mode_equals_one_file_at_a_time(tmp_path):
+    """`sela -E/-D out_dir files...`: many files in one process (pinned staging reused per worker thread,
+    files on the GPU one after the other).  Same bytes as one process per file; a bad file is reported
+    and does not stop the rest."""
+    _ensure_built()
+    cases = _cases(tmp_path)
+    for i in range(6):   # enough files that every worker thread reuses its staging buffers
+        wavio.write_wav(tmp_path / ("s%d.wav" % i), synth.sine_noise(44100, 2, n_frames=3 + 2 * i, seed=40 + i), 44100)
+        cases["s%d" % i] = tmp_path / ("s%d.wav" % i)
+    (tmp_path / "junk.wav").write_bytes(b"not a wav file at all, but long enough to pass the size check....")
+    enc, dec = tmp_path / "enc", tmp_path / "dec"
+    enc.mkdir()
+    dec.mkdir()
+    wavs = [cases[k] for k in sorted(cases)]
+    p = _run(BIN / "sela", "-E", enc, *wavs, tmp_path / "junk.wav", ok=False, env={"SELA_B200_WORKERS": "3"})
+    assert p.returncode == 1 and "junk.wav: chunkId is not RIFF" in p.stderr, (p.stdout, p.stderr)
+    assert "Encoded %d of %d files" % (len(wavs), len(wavs) + 1) in p.stdout
+    p = _run(BIN / "sela", "-D", dec, *[enc / (w.stem + ".sela") for w in wavs], env={"SELA_B200_WORKERS": "3"})
+    assert "Decoded %d of %d files" % (len(wavs), len(wavs)) in p.stdout
+    for w in wavs:
+        _run(BIN / "sela", "-e", w, tmp_path / "one.sela")
+        _run(BIN / "sela", "-d", tmp_path / "one.sela", tmp_path / "one.wav")
+        assert (enc / (w.stem + ".sela")).read_bytes() == (tmp_path / "one.sela").read_bytes(), w.name
+        assert (dec / (w.stem + ".wav")).read_bytes() == (tmp_path / "one.wav").read_bytes(), w.name

@@ -80,6 +80,37 @@ struct Context {
     unsigned long long *h_totals = nullptr;        // pinned: arena fill level after each chunk
 } g;
 
+// What a container handle owns besides the walk result: the device image of the bytes, a pinned
+// descriptor table and the upload events.  Recycled through a small free list, because a process
+// that decodes many files would otherwise pay cudaMalloc/cudaFree (a device-wide sync) and
+// cudaMallocHost/cudaFreeHost for every one of them.
+struct ContainerBuffers {
+    static constexpr int kPieces = 8;
+    void *d_bytes = nullptr;
+    size_t d_cap = 0;
+    selab200_subframe_desc *h_descs = nullptr;
+    size_t h_cap = 0; // descriptors
+    cudaEvent_t ev_piece[kPieces] = {};
+    void destroy()
+    {
+        for (cudaEvent_t &e : ev_piece)
+            if (e) {
+                cudaEventDestroy(e);
+                e = nullptr;
+            }
+        if (d_bytes)
+            cudaFree(d_bytes);
+        if (h_descs)
+            cudaFreeHost(h_descs);
+        d_bytes = nullptr;
+        h_descs = nullptr;
+        d_cap = h_cap = 0;
+    }
+};
+
+std::vector<ContainerBuffers> g_spare_buffers; // guarded by g_mutex
+constexpr size_t kMaxSpareBuffers = 16;
+
 // On every exit from a pipelined call -- error paths included -- nothing may still be
 // reading or writing the caller's host buffers.
 struct PipelineDrain {
@@ -352,6 +383,9 @@ void selab200_shutdown(void)
     if (!g.ready)
         return;
     cudaStreamSynchronize(g.stream);
+    for (ContainerBuffers &b : g_spare_buffers)
+        b.destroy();
+    g_spare_buffers.clear();
     g.in.release();
     g.descs.release();
     g.words.release();
@@ -693,10 +727,7 @@ struct selab200_container {
     const uint8_t *bytes = nullptr;
     size_t n_bytes = 0;
     selab200_container_info info{};
-    selab200_subframe_desc *h_descs = nullptr; // pinned, info.n_frames * channels
-    void *d_bytes = nullptr;                   // device image of the container (+ padding)
-    static constexpr int kPieces = 8;
-    cudaEvent_t ev_piece[kPieces] = {};
+    ContainerBuffers buf;
     size_t piece_bytes = 0;
     int n_pieces = 0;
 };
@@ -799,13 +830,10 @@ void selab200_container_close(selab200_container *h)
     std::lock_guard<std::mutex> lock(g_mutex);
     if (g.s_h2d)
         cudaStreamSynchronize(g.s_h2d); // the upload reads the caller's bytes
-    for (cudaEvent_t e : h->ev_piece)
-        if (e)
-            cudaEventDestroy(e);
-    if (h->d_bytes)
-        cudaFree(h->d_bytes);
-    if (h->h_descs)
-        cudaFreeHost(h->h_descs);
+    if (g.ready && g_spare_buffers.size() < kMaxSpareBuffers)
+        g_spare_buffers.push_back(h->buf);
+    else
+        h->buf.destroy();
     delete h;
 }
 
@@ -827,19 +855,40 @@ int selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_c
         h = new selab200_container;
         h->bytes = container;
         h->n_bytes = n_bytes;
+        // recycled buffers if a spare is large enough, else the largest spare grows
+        if (!g_spare_buffers.empty()) {
+            size_t pick = 0;
+            for (size_t i = 0; i < g_spare_buffers.size(); i++)
+                if (g_spare_buffers[i].d_cap >= n_bytes + 64 &&
+                    (g_spare_buffers[pick].d_cap < n_bytes + 64 || g_spare_buffers[i].d_cap < g_spare_buffers[pick].d_cap))
+                    pick = i;
+            h->buf = g_spare_buffers[pick];
+            g_spare_buffers.erase(g_spare_buffers.begin() + pick);
+        }
+        cudaError_t e = cudaSuccess;
+        if (h->buf.d_cap < n_bytes + 64) {
+            if (h->buf.d_bytes)
+                cudaFree(h->buf.d_bytes);
+            h->buf.d_bytes = nullptr;
+            h->buf.d_cap = 0;
+            const size_t want = n_bytes + n_bytes / 8 + 4096;
+            e = cudaMalloc(&h->buf.d_bytes, want);
+            if (e != cudaSuccess)
+                rc = fail(SELAB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            else
+                h->buf.d_cap = want;
+        }
         // start the upload first: the DMA engine streams the bytes while this thread walks them
-        cudaError_t e = cudaMalloc(&h->d_bytes, n_bytes + 64);
-        if (e != cudaSuccess)
-            rc = fail(SELAB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n_bytes + 64, cudaGetErrorString(e));
-        h->piece_bytes = ((n_bytes + selab200_container::kPieces - 1) / selab200_container::kPieces + 255) & ~(size_t)255;
+        h->piece_bytes = ((n_bytes + ContainerBuffers::kPieces - 1) / ContainerBuffers::kPieces + 255) & ~(size_t)255;
         for (int i = 0; rc == 0 && (size_t)i * h->piece_bytes < n_bytes; i++) {
             const size_t lo = (size_t)i * h->piece_bytes;
             const size_t len = lo + h->piece_bytes <= n_bytes ? h->piece_bytes : n_bytes - lo;
-            e = cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming);
+            if (!h->buf.ev_piece[i])
+                e = cudaEventCreateWithFlags(&h->buf.ev_piece[i], cudaEventDisableTiming);
             if (e == cudaSuccess)
-                e = cudaMemcpyAsync(static_cast<uint8_t *>(h->d_bytes) + lo, container + lo, len, cudaMemcpyHostToDevice, g.s_h2d);
+                e = cudaMemcpyAsync(static_cast<uint8_t *>(h->buf.d_bytes) + lo, container + lo, len, cudaMemcpyHostToDevice, g.s_h2d);
             if (e == cudaSuccess)
-                e = cudaEventRecord(h->ev_piece[i], g.s_h2d);
+                e = cudaEventRecord(h->buf.ev_piece[i], g.s_h2d);
             if (e != cudaSuccess)
                 rc = fail(SELAB200_ERR_CUDA, "container upload failed: %s", cudaGetErrorString(e));
             h->n_pieces = i + 1;
@@ -852,11 +901,19 @@ int selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_c
         descs.reserve(n_bytes / 2048 + 16);
         rc = walk_container(container, n_bytes, &h->info, &descs);
         if (rc == 0 && !descs.empty()) {
-            const size_t bytes = descs.size() * sizeof(selab200_subframe_desc);
-            if (cudaMallocHost(reinterpret_cast<void **>(&h->h_descs), bytes) != cudaSuccess)
-                rc = fail(SELAB200_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
-            else
-                memcpy(h->h_descs, descs.data(), bytes);
+            if (h->buf.h_cap < descs.size()) {
+                if (h->buf.h_descs)
+                    cudaFreeHost(h->buf.h_descs);
+                h->buf.h_descs = nullptr;
+                h->buf.h_cap = 0;
+                const size_t want = descs.size() + descs.size() / 4 + 64;
+                if (cudaMallocHost(reinterpret_cast<void **>(&h->buf.h_descs), want * sizeof(selab200_subframe_desc)) != cudaSuccess)
+                    rc = fail(SELAB200_ERR_CUDA, "cudaMallocHost(%zu) failed", want * sizeof(selab200_subframe_desc));
+                else
+                    h->buf.h_cap = want;
+            }
+            if (rc == 0)
+                memcpy(h->buf.h_descs, descs.data(), descs.size() * sizeof(selab200_subframe_desc));
         }
     }
     if (rc != 0) {
@@ -901,7 +958,7 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
     int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
     selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
     uint32_t *d_arena = static_cast<uint32_t *>(g.words.ptr);
-    const uint8_t *d_bytes = static_cast<const uint8_t *>(h->d_bytes);
+    const uint8_t *d_bytes = static_cast<const uint8_t *>(h->buf.d_bytes);
 
     CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
     CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
@@ -909,7 +966,7 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
         CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
-        const selab200_subframe_desc *dc = h->h_descs + (size_t)f0 * channels;
+        const selab200_subframe_desc *dc = h->buf.h_descs + (size_t)f0 * channels;
         const size_t chunk_sub = (size_t)nf * channels;
         cudaStream_t cs = g.s_compute[c % kLanes];
         DeviceBuffer &ws = g.lane_work[c % kLanes];
@@ -922,7 +979,7 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
         int piece = (int)(end_byte / h->piece_bytes);
         if (piece >= h->n_pieces)
             piece = h->n_pieces - 1;
-        CUDA_TRY(cudaStreamWaitEvent(cs, h->ev_piece[piece], 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->buf.ev_piece[piece], 0));
         k_container_unpack<<<(unsigned)((chunk_sub + 7) / 8), 256, 0, cs>>>(d_bytes, d_descs + (size_t)f0 * channels,
                                                                            (uint32_t)chunk_sub, channels,
                                                                            (unsigned long long)f0 * channels, d_arena);

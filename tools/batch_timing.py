@@ -46,6 +46,12 @@ for workers in (8, 16):
     out["batch_workers_%d" % workers] = {
         "encode_s": round(te, 3), "decode_s": round(td, 3),
         "encode_MSamples_s": round(out["samples"] / te / 1e6, 1), "decode_MSamples_s": round(out["samples"] / td / 1e6, 1)}
+# steady-state phases of one worker thread (SELA_B200_TIMING), last file of six
+e = dict(env, SELA_B200_WORKERS="1", SELA_B200_TIMING="1")
+r = subprocess.run([SELA, "-E", f"{D}/enc"] + wavs[:6], env=e, capture_output=True, text=True)
+out["one_worker_encode_phases_last_file"] = [l.replace("[sela_b200] ", "").split() for l in r.stderr.splitlines()[-4:]]
+r = subprocess.run([SELA, "-D", f"{D}/dec"] + [f"{D}/enc/f{i:04d}.sela" for i in range(6)], env=e, capture_output=True, text=True)
+out["one_worker_decode_phases_last_file"] = [l.replace("[sela_b200] ", "").split() for l in r.stderr.splitlines()[-5:]]
 # reference CLI, one process per file
 te = td = 0.0
 same = True

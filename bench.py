@@ -265,17 +265,24 @@ def run_ours(args, rank, world, local_rank):
     h_descs, p4 = pinned(n_frames * CHANNELS * 32, np.uint8)
     used = C.c_size_t(0)
 
+    split = [0.0, 0.0]   # seconds inside the encode call / the decode call (both synchronous)
+
     def e2e_step():
+        t_a = time.perf_counter()
         _lib.check(L.selab200_encode_frames(h_pcm.ctypes.data, n_frames, CHANNELS, h_descs.ctypes.data,
                                             h_words.ctypes.data, cap, C.addressof(used)))
+        t_b = time.perf_counter()
         _lib.check(L.selab200_decode_frames(h_descs.ctypes.data, n_frames, CHANNELS, h_words.ctypes.data,
                                             used.value, h_out.ctypes.data))
+        split[0] += t_b - t_a
+        split[1] += time.perf_counter() - t_b
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
         e2e_step()
     if dist:
         dist.barrier()
+    split[0] = split[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -313,7 +320,8 @@ def run_ours(args, rank, world, local_rank):
             "encode_ms": enc_ms, "decode_ms": dec_ms,
             "round_trip_bit_exact": round_trip_ok and e2e_ok,
             "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms_max, "steps": e2e_steps,
+                    "encode_ms": split[0] / e2e_steps * 1e3, "decode_ms": split[1] / e2e_steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",

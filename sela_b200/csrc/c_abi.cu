@@ -3,6 +3,7 @@
 // Host-side plumbing only: device selection, a grow-only device workspace, the
 // launches.  No algorithm lives here and there is no CPU fallback: without a
 // CUDA device every compute entry point returns SELAB200_ERR_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -64,7 +65,7 @@ struct DeviceBuffer {
     }
 };
 
-constexpr int kMaxChunks = 64;
+constexpr int kMaxChunks = 72;
 constexpr int kLanes = 8; // concurrent compute streams of the pipelined host calls
 
 struct Context {
@@ -149,6 +150,43 @@ uint32_t chunk_frames_for(uint32_t n_frames, uint32_t parts)
     while ((n_frames + c - 1) / c > (uint32_t)kMaxChunks)
         c *= 2;
     return c;
+}
+
+// Chunk boundaries of a pipelined host-buffer call.  Equal chunks; for the encoder the first and
+// the last are cut into shrinking pieces: what its pipeline cannot hide is the upload of the first
+// chunk before any kernel runs and the download of the last chunk after the last kernel, so those
+// two are made small (measured on the BASELINE batch: encode call 4.06 -> 3.93 ms; the decode call,
+// whose small chunks each pay the Rice kernel's fixed latency, gets slower and keeps equal chunks).
+// SELAB200_TAPER=0 switches it off.
+struct ChunkPlan {
+    std::vector<uint32_t> start; // n_chunks + 1 boundaries
+    uint32_t max_frames = 0;     // largest chunk (sizes the per-lane workspace)
+    uint32_t chunks() const { return (uint32_t)start.size() - 1; }
+};
+ChunkPlan plan_chunks(uint32_t n_frames, uint32_t parts, bool allow_taper)
+{
+    ChunkPlan p;
+    const uint32_t cf = chunk_frames_for(n_frames, parts);
+    const uint32_t n_base = (n_frames + cf - 1) / cf;
+    const char *env = std::getenv("SELAB200_TAPER");
+    const bool taper = allow_taper && !(env && env[0] == '0') && !std::getenv("SELAB200_CHUNK_FRAMES") && n_base >= 4 &&
+                       n_base + 6 <= (uint32_t)kMaxChunks;
+    p.start.push_back(0);
+    for (uint32_t c = 0; c < n_base; c++) {
+        const uint32_t f0 = c * cf, f1 = (f0 + cf <= n_frames) ? f0 + cf : n_frames, len = f1 - f0;
+        if (taper && c == 0 && len >= 512) {
+            p.start.push_back(f0 + len / 8);
+            p.start.push_back(f0 + len / 2);
+        } else if (taper && c == n_base - 1 && len >= 512) {
+            p.start.push_back(f0 + len / 2);
+            p.start.push_back(f0 + len / 2 + len / 4);
+            p.start.push_back(f0 + len / 2 + len / 4 + len / 8);
+        }
+        p.start.push_back(f1);
+    }
+    for (uint32_t c = 0; c + 1 < p.start.size(); c++)
+        p.max_frames = std::max(p.max_frames, p.start[c + 1] - p.start[c]);
+    return p;
 }
 
 const char *status_text(int s)
@@ -537,11 +575,11 @@ static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
     if (n_frames == 0)
         return 0;
     PipelineDrain drain;
-    const uint32_t cf = chunk_frames_for(n_frames, 8);
-    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
+    const ChunkPlan plan = plan_chunks(n_frames, 8, true);
+    const uint32_t n_chunks = plan.chunks();
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
-    const size_t ws_bytes = selab200_encode_workspace_bytes(cf, channels);
+    const size_t ws_bytes = selab200_encode_workspace_bytes(plan.max_frames, channels);
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(container_frame_byte(n_frames, channels, words_capacity) + 64)) return rc;
@@ -559,7 +597,7 @@ static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
     for (int i = 1; i < kLanes; i++)
         CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0;
         CUDA_TRY(cudaMemcpyAsync(d_pcm + (size_t)f0 * channels * kFrame, pcm + (size_t)f0 * channels * kFrame,
                                  nf * frame_bytes, cudaMemcpyHostToDevice, g.s_h2d));
         CUDA_TRY(cudaEventRecord(g.ev_h2d[c], g.s_h2d));
@@ -576,7 +614,7 @@ static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
     }
     g.h_totals[0] = 0;
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0;
         CUDA_TRY(cudaEventSynchronize(g.ev_done[c]));
         const unsigned long long lo = g.h_totals[c], hi = g.h_totals[c + 1];
         if (hi > words_capacity || hi < lo)
@@ -666,11 +704,11 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
     // Every chunk gets its own compute lane (up to kLanes): the Rice kernel is one lane per stream
     // and latency-bound (about 0.4 ms however small the chunk), so the chunks' Rice kernels must
     // overlap each other and the synthesis kernels of earlier chunks rather than queue up.
-    const uint32_t cf = chunk_frames_for(n_frames, 8);
-    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
+    const ChunkPlan plan = plan_chunks(n_frames, 8, false);
+    const uint32_t n_chunks = plan.chunks();
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
-    const size_t ws_bytes = selab200_decode_workspace_bytes(cf, channels);
+    const size_t ws_bytes = selab200_decode_workspace_bytes(plan.max_frames, channels);
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
     if (int rc = g.words.ensure(n_words * 4 + 16)) return rc;
@@ -686,7 +724,7 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
     for (int i = 1; i < kLanes; i++)
         CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0;
         // the words this chunk's descriptors reference (descriptors need not be in arena order)
         unsigned long long lo = ~0ull, hi = 0;
         const selab200_subframe_desc *dc = descs + (size_t)f0 * channels;
@@ -943,11 +981,11 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     PipelineDrain drain;
-    const uint32_t cf = chunk_frames_for(n_frames, 8);
-    const uint32_t n_chunks = (n_frames + cf - 1) / cf;
+    const ChunkPlan plan = plan_chunks(n_frames, 8, false);
+    const uint32_t n_chunks = plan.chunks();
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
-    const size_t ws_bytes = selab200_decode_workspace_bytes(cf, channels);
+    const size_t ws_bytes = selab200_decode_workspace_bytes(plan.max_frames, channels);
     const size_t n_words = (size_t)h->info.n_words;
     if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
     if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
@@ -965,7 +1003,7 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
     for (int i = 1; i < kLanes; i++)
         CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = c * cf, nf = (f0 + cf <= n_frames) ? cf : n_frames - f0;
+        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0;
         const selab200_subframe_desc *dc = h->buf.h_descs + (size_t)f0 * channels;
         const size_t chunk_sub = (size_t)nf * channels;
         cudaStream_t cs = g.s_compute[c % kLanes];

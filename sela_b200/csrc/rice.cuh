@@ -196,19 +196,83 @@ __device__ __noinline__ void warp_rice_pack(const int32_t *vals, int n, uint32_t
 // ever conflict).  Each lane keeps its own ring topped up with 16-byte loads from its own
 // stream (aligned down; the words in front of the stream are skipped, words past its end
 // read as zero -- bounded, unlike the reference), issued one batch ahead of use.
-// The parser's dependent chain per symbol is
-//     pos -> LDS pair -> funnel shift -> clz -> pos'   (+ LDS pair -> funnel shift -> brev for the payload)
-// and BATCH such steps run back to back with no votes and no branches; refills and the
-// all-done test happen at batch boundaries only.
-// Margins: a step consumes at most 2 words and looks 3 ahead, a batch 2*BATCH words; loads
-// issued at one boundary are committed at the next, so a lane needs 3 + 4*BATCH committed
-// words ahead of it at every boundary -- the top-up keeps about RING, and a lane that
-// still falls short (only streams running near 2 words per symbol can) refills on the spot.
+// The parser runs in symbol lockstep (see below): step n decodes symbol n of every lane, the
+// common case from a single 32-bit window; ring refills happen at batch boundaries only.
+// Margins: a fast step consumes at most one word and looks one ahead, the general parser tops the
+// ring up itself; loads issued at one boundary are committed at the next, so 3 + 4*BATCH committed
+// words ahead of a lane at every boundary is ample -- the top-up keeps about RING, and a lane
+// that still falls short refills on the spot.
 struct RiceLaneStream {
     const uint32_t *src;
     uint32_t n_words, k, count;
     int32_t *out;
 };
+
+// A lane's view of its stream and ring.  rb = ring + lane; vector v of vp holds words
+// [4v, 4v+4) counted from the 16-byte aligned base; words >= total read as zero.
+struct RiceRingView {
+    uint32_t *rb;
+    const uint4 *vp;
+    uint32_t nvec, total;
+};
+template <int RING>
+__device__ __forceinline__ uint4 ring_fetch(const RiceRingView &rv, uint32_t w) // words [w, w+4), w % 4 == 0
+{
+    return (w >> 2) < rv.nvec ? __ldg(rv.vp + (w >> 2)) : make_uint4(0, 0, 0, 0);
+}
+template <int RING>
+__device__ __forceinline__ void ring_commit(const RiceRingView &rv, uint32_t w, const uint4 v)
+{
+    const uint32_t r = (w & (RING - 1)) * 32;
+    const uint32_t x = w + 0 < rv.total ? v.x : 0u; // words past the stream's end read as zero
+    rv.rb[r] = x;
+    rv.rb[r + 32] = w + 1 < rv.total ? v.y : 0u;
+    rv.rb[r + 64] = w + 2 < rv.total ? v.z : 0u;
+    rv.rb[r + 96] = w + 3 < rv.total ? v.w : 0u;
+    if (r == 0)
+        rv.rb[RING * 32] = x; // mirror row: word w+1 is always one row below word w
+}
+template <int RING>
+__device__ __forceinline__ uint32_t ring_window(const uint32_t *rb, uint32_t at)
+{
+    const uint32_t r = ((at >> 5) & (RING - 1)) * 32;
+    return __funnelshift_r(rb[r], rb[r + 32], at);
+}
+
+// General parser for ONE symbol of any length starting at bit `pos` (the fast path handles symbols
+// that fit a 32-bit window).  Tops the ring up synchronously as it goes and leaves `ahead` committed
+// words in front of the new position.  Out of line on purpose: it runs for a handful of symbols per
+// stream at most, and eight inlined copies would quadruple the kernel.  Returns {u, pos, committed}.
+template <int RING>
+__device__ __noinline__ uint4 rice_slow_symbol(uint32_t *rb, const uint4 *vp, uint32_t nvec, uint32_t total,
+                                               uint32_t pos, uint32_t committed, uint32_t k, uint32_t ahead)
+{
+    const RiceRingView rv{rb, vp, nvec, total};
+    auto ensure = [&](uint32_t words_ahead) {
+        while (committed < (pos >> 5) + words_ahead) {
+            ring_commit<RING>(rv, committed, ring_fetch<RING>(rv, committed));
+            committed += 4;
+        }
+    };
+    uint32_t q = 0;
+    while (true) {
+        ensure(3);
+        const uint32_t ones = __clz(__brev(~ring_window<RING>(rb, pos))); // 32: no terminator in this window
+        q += ones;
+        if (ones < 32) {
+            pos += ones + 1;
+            break;
+        }
+        pos += 32;
+        if (pos > total * 32u + 64) // ran off the stream; words past the end read as zero, so the loop
+            break;                  // would end by itself one window later -- belt and braces
+    }
+    ensure(3);
+    const uint32_t payload = (__brev(ring_window<RING>(rb, pos)) >> 1) >> (31 - k);
+    pos += k;
+    ensure(ahead); // the fast steps that follow in this batch read ahead of pos without checking
+    return make_uint4((q << k) | payload, pos, committed, 0u); // uint32 shift as in rice_decoder.cpp:37
+}
 
 // Returns (per lane) false if the stream needed more bits than n_words holds.
 template <int RING, int BATCH>
@@ -224,20 +288,10 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
     const uint32_t total = st.n_words ? st.n_words + skip : 0; // words from the aligned base
     const uint32_t nvec = (total + 3) >> 2;
 
+    const RiceRingView rv{rb, vp, nvec, total};
     // fetch only ISSUES the load; nothing touches the value until commit, a batch later
-    auto fetch = [&](uint32_t w) -> uint4 { // words [w, w+4), w a multiple of 4
-        return (w >> 2) < nvec ? __ldg(vp + (w >> 2)) : make_uint4(0, 0, 0, 0);
-    };
-    auto commit = [&](uint32_t w, const uint4 v) {
-        const uint32_t r = (w & (RING - 1)) * 32;
-        const uint32_t x = w + 0 < total ? v.x : 0u; // words past the stream's end read as zero
-        rb[r] = x;
-        rb[r + 32] = w + 1 < total ? v.y : 0u;
-        rb[r + 64] = w + 2 < total ? v.z : 0u;
-        rb[r + 96] = w + 3 < total ? v.w : 0u;
-        if (r == 0)
-            rb[RING * 32] = x; // mirror row: word w+1 is always one row below word w
-    };
+    auto fetch = [&](uint32_t w) -> uint4 { return ring_fetch<RING>(rv, w); };
+    auto commit = [&](uint32_t w, const uint4 v) { ring_commit<RING>(rv, w, v); };
     uint32_t loaded = 0;    // words [.., loaded) have been requested
     uint32_t committed = 0; // words [.., committed) are in the ring
     for (; loaded < RING; loaded += 32) { // initial fill, eight loads in flight at a time
@@ -251,32 +305,57 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
     }
     committed = loaded;
 
-    uint32_t pos = skip * 32, i = 0, q_acc = 0, produced = 0;
+    // ---- symbol-lockstep parser --------------------------------------------------------------
+    // Step n decodes symbol n of EVERY lane's stream, so the output index, the store schedule and
+    // the loop bound are warp-uniform and only `pos` (and the ring fill) are per-lane state.
+    // Fast path: the whole symbol (ones, terminator, k payload bits) lies inside ONE 32-bit window
+    //     pos -> LDS pair -> funnel shift -> brev -> clz -> pos'
+    // with the payload cut from the same window.  A lane whose symbol is longer than the window
+    // (a unary run of 32 - k ones or more: rare) flags the step; if any lane did, those lanes redo
+    // the symbol with the general, refilling parser under a (divergent) branch.
+    uint32_t pos = skip * 32;
     const uint32_t k = st.k, count = st.count;
-    const uint32_t kshift = 31 - k; // payload = (brev(win) >> 1) >> (31 - k), valid for k = 0 too
-    bool done = count == 0;
-    int32_t o0 = 0, o1 = 0, o2 = 0;
+    const uint32_t kshift = 31 - k; // payload = (t >> 1) >> (31 - k), valid for k = 0 too
+    uint32_t max_count = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(kFull, max_count, o);
+        max_count = other > max_count ? other : max_count;
+    }
     const bool vec_out = (reinterpret_cast<uintptr_t>(st.out) & 15) == 0;
     uint4 pend0 = make_uint4(0, 0, 0, 0), pend1 = pend0;
     uint32_t n_pend = 0; // per lane: 0, 1 or 2 vectors in flight, for words [committed, committed + 4*n_pend)
+    auto window = [&](uint32_t at) -> uint32_t { return ring_window<RING>(rb, at); };
+    auto slow_symbol = [&]() -> uint32_t {
+        if (n_pend > 0) // the general parser commits on its own: retire what is in flight first
+            commit(committed, pend0);
+        if (n_pend > 1)
+            commit(committed + 4, pend1);
+        committed += 4 * n_pend;
+        n_pend = 0;
+        const uint4 r = rice_slow_symbol<RING>(rb, vp, nvec, total, pos, committed, k, kNeed);
+        pos = r.y;
+        committed = r.z;
+        loaded = loaded > committed ? loaded : committed;
+        return r.x;
+    };
 
-    while (true) {
-        // ---- batch boundary (per-lane, predicated; the only vote is the exit test) ----
+    for (uint32_t n = 0; n < max_count; n += BATCH) {
+        // ---- batch boundary (per lane, predicated) ----
+        const bool live = n < count;
         if (n_pend > 0)
             commit(committed, pend0);
         if (n_pend > 1)
             commit(committed + 4, pend1);
         committed += 4 * n_pend;
         n_pend = 0;
-        if (!__any_sync(kFull, !done))
-            break;
         const uint32_t wi = pos >> 5;
-        while (!done && committed < wi + kNeed) { // rare: this lane outran its top-up
+        while (live && committed < wi + kNeed) { // rare: this lane outran its top-up
             commit(committed, fetch(committed));
             committed += 4;
             loaded = committed;
         }
-        if (!done && loaded + 4 <= wi + RING) { // room for one more vector without touching unread words
+        if (live && loaded + 4 <= wi + RING) { // room for one more vector without touching unread words
             pend0 = fetch(loaded);
             loaded += 4;
             n_pend = 1;
@@ -286,58 +365,38 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
                 n_pend = 2;
             }
         }
-        // ---- BATCH parser steps: a whole symbol each, or 32 more ones of a long unary run ----
-        // Two passes over the batch.  Pass 1 is the serial recurrence and nothing else:
-        //   pos -> LDS pair -> funnel shift -> clz -> pos'
-        // Pass 2 (payload bits, un-zig-zag, stores) has no dependence between steps, so its
-        // shared-memory latencies overlap instead of queueing behind the recurrence.
-        uint32_t p2s[BATCH], qs[BATCH];
-        bool emits[BATCH];
+        // ---- BATCH symbols ----
+        int32_t v[BATCH];
 #pragma unroll
-        for (int s = 0; s < BATCH; s++) {
-            const uint32_t ra = ((pos >> 5) & (RING - 1)) * 32;
-            const uint32_t inv = ~__funnelshift_r(rb[ra], rb[ra + 32], pos);
-            const uint32_t ones = __clz(__brev(inv));  // 32 when the window is all ones
-            const uint32_t run = ones >> 5;             // 1: no terminator in this window
-            const uint32_t p2 = pos + ones + 1 - run;
-            const uint32_t q = q_acc + ones;
-            p2s[s] = p2;
-            qs[s] = q;
-            emits[s] = !done && !run;
-            if (!done) {
-                q_acc = run ? q : 0;
-                pos = run ? p2 : p2 + k;
+        for (int e = 0; e < BATCH; e++) {
+            const bool active = n + e < count;
+            const uint32_t b = __brev(window(pos));
+            const uint32_t ones = __clz(~b);        // trailing ones of the window (32: all ones)
+            const uint32_t len = ones + 1 + k;
+            const bool need_slow = active && len > 32;
+            const uint32_t t = __funnelshift_lc(0u, b, ones + 1); // b << (ones + 1), 0 for a shift of 32
+            uint32_t u = (ones << k) | ((t >> 1) >> kshift);
+            if (__any_sync(kFull, need_slow)) {
+                if (need_slow)
+                    u = slow_symbol();
+                else if (active)
+                    pos += len;
+            } else if (active) {
+                pos += len;
             }
-            produced += emits[s];
-            done = done || produced == count;
+            v[e] = unzigzag(u);
         }
+        // ---- stores: symbols n .. n+BATCH-1 of this lane's row ----
+        if (n + BATCH <= count && vec_out) {
 #pragma unroll
-        for (int s = 0; s < BATCH; s++) {
-            const uint32_t rc = ((p2s[s] >> 5) & (RING - 1)) * 32;
-            const uint32_t win = __funnelshift_r(rb[rc], rb[rc + 32], p2s[s]);
-            const uint32_t payload = (__brev(win) >> 1) >> kshift;
-            const int32_t v = unzigzag((qs[s] << k) | payload); // uint32 shift as in rice_decoder.cpp:37
-            const bool emit = emits[s];
-            const uint32_t sel = i & 3u;
-            if (vec_out) {
-                if (emit && sel == 3)
-                    *reinterpret_cast<int4 *>(st.out + i - 3) = make_int4(o0, o1, o2, v);
-                if (emit) {
-                    o0 = sel == 0 ? v : o0;
-                    o1 = sel == 1 ? v : o1;
-                    o2 = sel == 2 ? v : o2;
-                }
-            } else if (emit) {
-                st.out[i] = v;
-            }
-            i += emit;
+            for (int e = 0; e < BATCH; e += 4)
+                *reinterpret_cast<int4 *>(st.out + n + e) = make_int4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < BATCH; e++)
+                if (n + e < count)
+                    st.out[n + e] = v[e];
         }
-    }
-    if (vec_out && count) {
-        const uint32_t rem = count & 3u, b = count - rem;
-        if (rem > 0) st.out[b] = o0;
-        if (rem > 1) st.out[b + 1] = o1;
-        if (rem > 2) st.out[b + 2] = o2;
     }
     return pos <= total * 32u;
 }

@@ -12,5 +12,6 @@ for rep in range(reps):
             print(var, v, "FAILED", r.stderr[-300:])
             continue
         e = d["e2e"]
-        print("%s=%s  device %.3f ms  e2e %.3f ms (encode %.3f + decode %.3f)  exact %s" % (
-            var, v, d["ms_per_step"], e["ms_per_step"], e["encode_ms"], e["decode_ms"], d["round_trip_bit_exact"]), flush=True)
+        print("%s=%s  device %.3f ms (encode %.3f + decode %.3f)  e2e %.3f ms (encode %.3f + decode %.3f)  exact %s" % (
+            var, v, d["ms_per_step"], d["encode_ms"], d["decode_ms"], e["ms_per_step"], e["encode_ms"], e["decode_ms"],
+            d["round_trip_bit_exact"]), flush=True)

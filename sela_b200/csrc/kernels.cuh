@@ -572,7 +572,7 @@ __global__ void k_synthesise(DecodeParams p)
 __device__ __forceinline__ int order_class(int order) { return order <= 28 ? 0 : order <= 56 ? 1 : 2; }
 
 // One CTA: stable counting sort of the subframes by class into p.order_index; every class segment
-// starts on a warp boundary (4 subframes), gaps hold 0xffffffff (pre-set by the host side).
+// starts on a warp boundary (4 subframes), widest class first; gaps hold 0xffffffff (pre-set by the host side).
 __global__ void __launch_bounds__(1024) k_decode_classify(DecodeParams p)
 {
     __shared__ unsigned long long warp_tot[32]; // four 16-bit class counts per warp
@@ -602,8 +602,11 @@ __global__ void __launch_bounds__(1024) k_decode_classify(DecodeParams p)
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t per_warp = 4 / gsz; // units per warp
+        // widest class first: a synthesis warp runs its four subframes start to finish (hundreds of
+        // microseconds), so the longest-running warps must be scheduled first and the short ones
+        // left to fill the tail
         uint32_t base = 0;
-        for (int c = 0; c < 4; c++) {
+        for (int c = 3; c >= 0; c--) {
             run[c] = base;
             base += (count[c] + per_warp - 1) / per_warp * per_warp;
         }

@@ -640,7 +640,9 @@ void SelaFile::readFromFile(std::ifstream &inputFile)
         return w;
     };
     selaFrames.clear();
-    selaFrames.reserve(selaHeader.numFrames);
+    // numFrames is only a promise: never reserve more frames than the bytes could hold
+    selaFrames.reserve(std::min<size_t>(selaHeader.numFrames,
+                                        contents.size() / (4 + 12 * std::max<size_t>(1, selaHeader.channels))));
     for (uint32_t f = 0; f < selaHeader.numFrames; f++) {
         if (at + 4 > contents.size() || rd.u32(at) != 0xAA55FF00u)
             break;

@@ -176,3 +176,47 @@ def test_full_baseline_container_round_trip(O):
     assert ours.tobytes() == wavio.pack_container(d_ref, w_ref, 44100, 2)
     info, out = codec.decode_container(ours)
     assert info["n_frames"] == 12919 and np.array_equal(out, pcm.reshape(-1))
+
+
+def test_walker_agrees_with_the_value_struct_reader_on_damaged_files(O, tmp_path):
+    """Two parsers read .sela bytes: file::SelaFile::readFromFile of the C++ mirror (builds the
+    reference's value structs) and the library's copy-free walk.  On truncated / corrupted input they
+    must agree: same error message, or the same frames -- checked through the bytes the struct reader
+    writes back (header + exactly the frames it accepted)."""
+    host_bin = ROOT / "sela_b200" / "host" / "bin" / "container_check"
+    if not host_bin.exists():
+        subprocess.run(["make", "-C", str(ROOT / "sela_b200" / "host")], check=True, capture_output=True)
+    pcm = _stereo(5, 7)
+    blob, _, _ = _blob(O, pcm, 2)
+    mono, _, _ = _blob(O, synth.sine_noise(8000, 1, n_frames=3, seed=9), 1, 8000)
+    rng = np.random.default_rng(77)
+    cases = []
+    for base in (blob, mono):
+        n = len(base)
+        cases += [base[:c] for c in sorted(set(int(v) for v in rng.integers(0, n, 24)) | {0, 3, 14, 15, 16, 18, 19, 26, n - 1})]
+        for _ in range(24):                     # one flipped byte: header fields, sync words, counts, payload
+            b = bytearray(base)
+            at = int(rng.integers(0, n)) if rng.random() < 0.5 else int(rng.integers(0, 64))
+            b[at] ^= 1 << int(rng.integers(0, 8))
+            cases.append(bytes(b))
+        huge = bytearray(base)
+        huge[11:15] = b"\xff\xff\xff\xff"       # a frame count no file could hold
+        cases.append(bytes(huge))
+    agree = 0
+    for i, case in enumerate(cases):
+        (tmp_path / "in.sela").write_bytes(case)
+        p = subprocess.run([str(host_bin), "sela", str(tmp_path / "in.sela"), str(tmp_path / "out.sela")],
+                           capture_output=True, text=True, timeout=60)
+        try:
+            info = codec.container_info(case)
+            err = None
+        except SelaB200Error as e:
+            info, err = None, str(e)
+        if p.returncode != 0:
+            assert err is not None and p.stderr.strip() in err, (i, p.stderr, err)
+        else:
+            assert err is None, (i, err)
+            back = (tmp_path / "out.sela").read_bytes()
+            assert len(back) == info["n_bytes_used"] and back == case[:len(back)], (i, len(back), info)
+        agree += 1
+    assert agree == len(cases)

@@ -866,6 +866,8 @@ void selab200_container_close(selab200_container *h)
     if (!h)
         return;
     std::lock_guard<std::mutex> lock(g_mutex);
+    if (g.ready)
+        cudaSetDevice(g.device); // the caller may be on a thread that never selected the device
     if (g.s_h2d)
         cudaStreamSynchronize(g.s_h2d); // the upload reads the caller's bytes
     if (g.ready && g_spare_buffers.size() < kMaxSpareBuffers)
@@ -893,7 +895,7 @@ int selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_c
         h = new selab200_container;
         h->bytes = container;
         h->n_bytes = n_bytes;
-        // recycled buffers if a spare is large enough, else the largest spare grows
+        // recycled buffers: the smallest spare that is large enough, else any spare (it is regrown below)
         if (!g_spare_buffers.empty()) {
             size_t pick = 0;
             for (size_t i = 0; i < g_spare_buffers.size(); i++)

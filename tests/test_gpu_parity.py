@@ -359,3 +359,46 @@ def test_config4_shape_bit_exact(O):
     assert d.tobytes() == d_ref.tobytes() and np.array_equal(w, w_ref)
     assert not d["subframe_type"].any()          # more than two channels: no difference coding
     assert np.array_equal(sela_b200.decode_frames(d, w, 8), pcm.reshape(-1))
+
+
+def _rice_pack_bits(us, k):
+    """Bit-serial restatement of rice_encoder.cpp:35-71 for a CHOSEN k (the encoder's own search
+    never picks most of these): u >> k ones, a zero, the k low bits MSB first; bit b -> word b/32, bit b%32."""
+    bits = []
+    for u in us:
+        bits += [1] * (u >> k) + [0] + [(u >> (k - 1 - j)) & 1 for j in range(k)]
+    bits += [0] * (-len(bits) % 32)
+    b = np.array(bits, np.uint64).reshape(-1, 32)
+    return (b << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+
+
+def test_rice_decode_window_boundaries_for_every_k(O):
+    """The parser's fast path takes a symbol that fits one 32-bit window (ones + 1 + k <= 32) and hands
+    anything longer to the general parser: walk the boundary for every k, at every bit alignment, with
+    runs of exactly 31/32/33/63/64/65 ones, against the reference's decoder."""
+    rng = np.random.default_rng(5)
+    rows = []
+    for k in (0, 1, 2, 5, 11, 12, 19, 20, 24, 30, 31):
+        edge = [0, 1, max(31 - k - 1, 0), 31 - k, 32 - k, 33 - k if k < 33 else 0, 31, 32, 33, 63, 64, 65, 100]
+        qs = []
+        for shift in range(0, 37, 3):                      # slide the boundary cases through the bit alignments
+            qs += [1] * (shift % 5) + [q for q in edge if q >= 0]
+        qs += [int(v) for v in rng.integers(0, 6, 300)]    # ordinary symbols behind them
+        us = []
+        for q in qs:
+            q = min(q, (0xffffffff >> k)) if k else q      # keep (q << k) inside 32 bits: the value itself is tested elsewhere
+            us.append((q << k) | int(rng.integers(0, 1 << k)) if k else q)
+        rows.append((k, us, _rice_pack_bits(us, k)))
+    stride = max(r[2].size for r in rows)
+    words = np.zeros((len(rows), stride), np.uint32)
+    for i, (_, _, w) in enumerate(rows):
+        words[i, :w.size] = w
+    ks = np.array([r[0] for r in rows], np.uint32)
+    counts = np.array([len(r[1]) for r in rows], np.uint32)
+    nw = np.array([r[2].size for r in rows], np.uint32)
+    out = sela_b200.rice_decode(words, nw, ks, counts, out_stride=int(counts.max()))
+    for i, (k, us, w) in enumerate(rows):
+        ref = O.rice_decode(w, k, len(us))
+        assert np.array_equal(out[i, :len(us)], ref), k
+        want = np.array([(u >> 1) ^ -(u & 1) for u in us], np.int64).astype(np.int32)
+        assert np.array_equal(ref, want), k            # and the reference agrees with the textbook inverse

@@ -122,7 +122,8 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
  * selab200_status once the stream has drained; d_words_used is a device uint64.
  * workspace: selab200_*_workspace_bytes() bytes of device memory, 256-aligned.  d_words must be
  * 16-byte aligned and readable up to the next 16-byte boundary past its last word (the Rice
- * decoder fetches 16 bytes at a time); cudaMalloc / torch allocations satisfy both. */
+ * decoder fetches 16 bytes at a time); cudaMalloc / torch allocations satisfy both.  d_pcm (stereo) must
+ * be 16-byte aligned as well. */
 size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels);
 int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels,
                                   selab200_subframe_desc *d_descs, uint32_t *d_words,
@@ -142,6 +143,10 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
 int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_t n_frames,
                                        uint32_t channels, const uint32_t *d_words, size_t n_words,
                                        int32_t *d_residues, int32_t *d_status, void *stream);
+/* How many streams of the last selab200_rice_decode_frames_device call the fast decoder handed to the
+ * general lane-per-stream parser (streams it could not split, or that hold a symbol its windows do not
+ * cover; results are identical either way).  Synchronises.  Diagnostics / bench bookkeeping. */
+int selab200_rice_decode_flagged(uint32_t *n_flagged);
 
 /* ------------------------------------------------ .sela container level -- */
 

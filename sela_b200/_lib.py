@@ -62,6 +62,7 @@ _SIGNATURES = {
     "selab200_decode_workspace_bytes": (_SZ, [_U32, _U32]),
     "selab200_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V, _SZ, _V]),
     "selab200_rice_decode_frames_device": (_I, [_V, _U32, _U32, _V, _SZ, _V, _V, _V]),
+    "selab200_rice_decode_flagged": (_I, [_V]),
     "selab200_container_bound": (_SZ, [_U32, _U32]),
     "selab200_encode_container": (_I, [_V, _U32, _U32, _U32, C.c_uint16, _V, _SZ, _V]),
     "selab200_container_info_get": (_I, [_V, _SZ, _V]),

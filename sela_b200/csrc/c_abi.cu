@@ -79,6 +79,8 @@ struct Context {
     DeviceBuffer in, descs, words, work, lane_work[kLanes], aux, small;
     int32_t *h_small = nullptr;                    // pinned: [0] status, [2..3] words_used
     unsigned long long *h_totals = nullptr;        // pinned: arena fill level after each chunk
+    size_t last_rice_n_sub = 0;                    // selab200_rice_decode_frames_device bookkeeping (flag count query)
+    cudaStream_t last_rice_stream = nullptr;
 } g;
 
 // What a container handle owns besides the walk result: the device image of the bytes, a pinned
@@ -212,10 +214,27 @@ int require_ready()
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Raises a kernel's dynamic shared-memory limit; remembered per (kernel, device): the attribute call is a
+// host round trip that would otherwise precede every launch.
 template <typename K>
 int set_smem(K kernel, size_t bytes)
 {
+    static std::mutex m;
+    static std::vector<std::pair<std::pair<const void *, int>, size_t>> done;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    const std::pair<const void *, int> key(reinterpret_cast<const void *>(kernel), dev);
+    std::lock_guard<std::mutex> lock(m);
+    for (auto &e : done)
+        if (e.first == key) {
+            if (e.second >= bytes)
+                return 0;
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return 0;
+        }
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done.emplace_back(key, bytes);
     return 0;
 }
 
@@ -305,6 +324,82 @@ int launch_rice_decode(const DecodeParams &p, int which, cudaStream_t stream)
     return launch_check(which ? "k_rice_decode(res)" : "k_rice_decode(refl)");
 }
 
+// Residue streams (K5 proper).  Large batches: one lane per stream through k_rice_decode_vs.  Smaller
+// ones: every stream is cut into S parts first (k_rice_split_index), so that a batch of BASELINE's
+// size still fills the machine.  SELAB200_RICE_SPLIT = 0 (first-generation kernel only), 1, 2, 4, 8, 16
+// overrides the choice.  aux: n_sub * 64 bytes (split table + per-stream flags).
+int rice_split_log2(size_t n_sub)
+{
+    if (const char *env = std::getenv("SELAB200_RICE_SPLIT")) {
+        const long v = std::atol(env);
+        if (v <= 0)
+            return -1;
+        int l = 0;
+        while ((1 << (l + 1)) <= v && l < 4)
+            l++;
+        return l;
+    }
+    int l = 0;
+    while (l < 4 && (n_sub << l) < (size_t)180000)
+        l++;
+    return l;
+}
+
+template <int LOG2S>
+int launch_split_index(const RiceVsParams &q, size_t n_sub, cudaStream_t stream)
+{
+    constexpr int W = 32 >> LOG2S, kWarps = 2;
+    const size_t smem = rice_split_smem_bytes(LOG2S, q.cap_words, kWarps);
+    if (int rc = set_smem(k_rice_split_index<LOG2S>, smem))
+        return rc;
+    const unsigned blocks = (unsigned)((n_sub + W * kWarps - 1) / (W * kWarps));
+    k_rice_split_index<LOG2S><<<blocks, 32 * kWarps, smem, stream>>>(q);
+    return launch_check("k_rice_split_index");
+}
+
+int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
+{
+    const size_t n_sub = (size_t)p.n_frames * p.channels;
+    const int log2s = rice_split_log2(n_sub);
+    if (log2s < 0 || (reinterpret_cast<uintptr_t>(p.ws_res) & 15) != 0)
+        return launch_rice_decode(p, 1, stream);
+    RiceVsParams q;
+    q.descs = p.descs;
+    q.n_sub = (uint32_t)n_sub;
+    q.channels = p.channels;
+    q.words = p.words;
+    q.n_words = p.n_words;
+    q.out = p.ws_res;
+    q.table = static_cast<uint32_t *>(aux);
+    q.flags = q.table + n_sub * 15;
+    q.status = p.status;
+    q.cap_words = 1152;
+    if (const char *env = std::getenv("SELAB200_RICE_SPLIT_CAP")) {
+        const long v = std::atol(env);
+        if (v >= 64 && v <= 8192)
+            q.cap_words = (uint32_t)(v & ~3l);
+    }
+    int rc = 0;
+    switch (log2s) {
+    case 0: CUDA_TRY(cudaMemsetAsync(q.flags, 0, n_sub * 4, stream)); break;
+    case 1: rc = launch_split_index<1>(q, n_sub, stream); break;
+    case 2: rc = launch_split_index<2>(q, n_sub, stream); break;
+    case 3: rc = launch_split_index<3>(q, n_sub, stream); break;
+    default: rc = launch_split_index<4>(q, n_sub, stream); break;
+    }
+    if (rc)
+        return rc;
+    if (int rc2 = set_smem(k_rice_decode_vs, kVsSmemBytes))
+        return rc2;
+    const size_t n_vs = n_sub << log2s;
+    k_rice_decode_vs<<<(unsigned)((n_vs + 32 * kVsWarps - 1) / (32 * kVsWarps)), 32 * kVsWarps, kVsSmemBytes, stream>>>(q, log2s);
+    if (int rc2 = launch_check("k_rice_decode_vs"))
+        return rc2;
+    DecodeParams pf = p; // whatever was flagged: the general lane-per-stream parser decodes it again
+    pf.rice_flags = q.flags;
+    return launch_rice_decode(pf, 1, stream);
+}
+
 int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint32_t channels,
                   const uint32_t *d_words, size_t n_words, int16_t *d_pcm, int32_t *d_status, void *d_ws,
                   size_t ws_bytes, cudaStream_t stream, bool fresh = true)
@@ -329,6 +424,8 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     p.ws_q = static_cast<int32_t *>(d_ws);
     p.ws_res = reinterpret_cast<int32_t *>(static_cast<char *>(d_ws) + align256(n_sub * 128 * 4));
     p.order_index = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(p.ws_res) + align256(n_sub * kFrame * 4));
+    p.rice_flags = nullptr;
+    void *rice_aux = reinterpret_cast<char *>(p.order_index) + align256((n_sub + 16) * 4);
     const size_t n_slots = (n_sub + 12 + 3) / 4 * 4; // every class segment starts on a warp boundary
     CUDA_TRY(cudaMemsetAsync(p.order_index, 0xff, n_slots * 4, stream));
     k_decode_classify<<<1, 1024, 0, stream>>>(p);
@@ -336,7 +433,7 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
         return rc;
     if (int rc = launch_rice_decode(p, 0, stream))
         return rc;
-    if (int rc = launch_rice_decode(p, 1, stream))
+    if (int rc = launch_rice_residues(p, rice_aux, stream))
         return rc;
     p.fallback_only = 1;
     k_synthesise_quad<<<(unsigned)(n_slots / 4), 32, 0, stream>>>(p);
@@ -492,7 +589,7 @@ size_t selab200_encode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 size_t selab200_decode_workspace_bytes(uint32_t n_frames, uint32_t channels)
 {
     const size_t n_sub = (size_t)n_frames * channels;
-    return align256(n_sub * 128 * 4) + align256(n_sub * kFrame * 4) + align256((n_sub + 16) * 4) + 256;
+    return align256(n_sub * 128 * 4) + align256(n_sub * kFrame * 4) + align256((n_sub + 16) * 4) + align256(n_sub * 64) + 256;
 }
 
 int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels,
@@ -556,7 +653,33 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
     p.ws_res = d_residues;
     p.order_index = nullptr;
     p.fallback_only = 0;
-    return launch_rice_decode(p, 1, (cudaStream_t)stream);
+    p.rice_flags = nullptr;
+    if (int rc = g.aux.ensure((size_t)n_frames * channels * 64 + 256))
+        return rc;
+    g.last_rice_n_sub = (size_t)n_frames * channels;
+    g.last_rice_stream = (cudaStream_t)stream;
+    return launch_rice_residues(p, g.aux.ptr, (cudaStream_t)stream);
+}
+
+int selab200_rice_decode_flagged(uint32_t *n_flagged)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!n_flagged)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    *n_flagged = 0;
+    const size_t n = g.last_rice_n_sub;
+    if (n == 0 || g.aux.bytes < n * 64)
+        return 0;
+    std::vector<uint32_t> flags(n);
+    CUDA_TRY(cudaStreamSynchronize(g.last_rice_stream));
+    CUDA_TRY(cudaMemcpy(flags.data(), static_cast<uint32_t *>(g.aux.ptr) + n * 15, n * 4, cudaMemcpyDeviceToHost));
+    uint32_t c = 0;
+    for (uint32_t f : flags)
+        c += f != 0;
+    *n_flagged = c;
+    return 0;
 }
 
 // Bytes of container in front of frame f when `words` Rice words precede it.

@@ -13,6 +13,7 @@
 
 #include "lpc.cuh"
 #include "rice.cuh"
+#include "rice_vs.cuh"
 
 namespace selab200 {
 
@@ -427,6 +428,7 @@ struct DecodeParams {
     int32_t *ws_res; // [n_sub][2048]
     uint32_t *order_index; // [n_sub + 16]: subframe ids grouped by predictor-order class (k_decode_classify)
     int fallback_only;
+    const uint32_t *rice_flags; // residue pass of k_rice_decode: when set, only streams with a non-zero flag (rice_vs.cuh)
 };
 
 // K5: one lane per stream, 2 warps per CTA.  which = 0: reflection streams (-> ws_q), 1: residue
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p,
             st.k = d.refl_rice_param;
             st.count = d.lpc_order;
             st.out = p.ws_q + (size_t)sub * 128;
-        } else {
+        } else if (!p.rice_flags || p.rice_flags[sub]) {
             st.src = p.words + d.res_offset;
             st.n_words = d.res_words;
             st.k = d.res_rice_param;
@@ -463,6 +465,8 @@ __global__ void __launch_bounds__(32 * kRiceWarps) k_rice_decode(DecodeParams p,
             st.out = p.ws_res + (size_t)sub * kFrame;
         }
     }
+    if (which == 1 && p.rice_flags && __ballot_sync(kFull, st.count != 0) == 0)
+        return; // nothing flagged in this warp (the usual case)
     if (!warp_rice_decode32<RING, BATCH>(ring[warp_id()], st))
         raise_status(p.status, SELAB200_ERR_BITSTREAM);
 }

@@ -56,3 +56,33 @@ class DeviceCodec:
         for what, s in zip(("encode", "decode"), st):
             if s != 0:
                 raise SelaB200Error(s, "%s kernel reported %s" % (what, STATUS_NAMES.get(s, s)))
+
+
+def rice_decode_frames(descs, words, channels, device=0):
+    """Residue streams of every subframe -> int32 [n_sub, 2048] (the Rice-decode kernel on its own,
+    selab200_rice_decode_frames_device).  descs: numpy array of DESC_DTYPE, words: uint32 arena.
+    Returns (residues, n_flagged)."""
+    import numpy as np
+    from ._lib import DESC_DTYPE
+    init(device)
+    dev = torch.device("cuda", device)
+    L = lib()
+    n_sub = descs.size
+    assert n_sub % channels == 0
+    d_descs = torch.from_numpy(np.ascontiguousarray(descs).view(np.uint8).reshape(-1).copy()).to(dev)
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    d_words = torch.zeros(w.size + 8, dtype=torch.int32, device=dev)
+    d_words[:w.size] = torch.from_numpy(w.view(np.int32)).to(dev)
+    out = torch.empty(n_sub * FRAME, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    check(L.selab200_rice_decode_frames_device(d_descs.data_ptr(), n_sub // channels, channels, d_words.data_ptr(),
+                                               w.size, out.data_ptr(), status.data_ptr(), C.c_void_p(stream)))
+    torch.cuda.synchronize(dev)
+    st = int(status.item())
+    if st != 0:
+        from ._lib import SelaB200Error, STATUS_NAMES
+        raise SelaB200Error(st, "rice decode kernel reported %s" % STATUS_NAMES.get(st, st))
+    flagged = C.c_uint32(0)
+    check(L.selab200_rice_decode_flagged(C.addressof(flagged)))
+    return out.cpu().numpy().reshape(n_sub, FRAME), flagged.value

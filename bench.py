@@ -100,6 +100,35 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def workload_config(n_frames, n_samples):
+    """The `config` object of BOTH arms (the driver compares them): what one GPU's workload is."""
+    return {"workload": WORKLOAD, "frames_per_gpu": n_frames, "samples_per_gpu": n_samples,
+            "l2": "no flush: per step the kernels stream the PCM, the word arena and the residue workspace of the "
+                  "whole file (about 390 MB), larger than the 126 MB L2"}
+
+
+def source_hash():
+    """Hash of the kernel sources: ties the ncu-derived numbers in profiles/traffic.json to the code that ran."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "sela_b200" / "csrc").glob("*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def measured_profile(kernel):
+    """What the committed ncu capture says about `kernel` (profiles/traffic.json): DRAM bytes per launch, pipe
+    utilisation.  Returns (entry or None, stale flag): stale = the kernel sources changed since the capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        doc = json.loads(p.read_text())
+        e = doc[kernel]
+        return e, doc.get("source_hash") != source_hash()
+    except Exception:
+        return None, True
+
+
 def measured_traffic(kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (cannot be taken
     inside the bench: a number measured under a profiler is never a bench value)."""
@@ -108,6 +137,206 @@ def measured_traffic(kernel):
         return int(json.loads(p.read_text())[kernel]["traffic"])
     except Exception:
         return None
+
+
+
+def rice_decode_roofline(codec, n_frames, n_words, dev, peak, tiles=(1, 16)):
+    """The Rice-decode kernel (K5) on its own, timed here with CUDA events through
+    selab200_rice_decode_frames_device: BASELINE's batch, and the same streams tiled to a batch that fills the
+    machine.  Algorithmic bytes: residue words read + 4 B per decoded sample written."""
+    import torch
+    from sela_b200 import _lib
+    L = _lib.lib()
+    descs = codec.descs.cpu().numpy().view(_lib.DESC_DTYPE).copy()
+    res_words = int(descs["res_words"].astype(np.int64).sum())
+    words = codec.words[:n_words]
+    out = {}
+    for tile in tiles:
+        d = np.tile(descs, tile)
+        for r in range(1, tile):
+            sl = slice(r * descs.size, (r + 1) * descs.size)
+            d["refl_offset"][sl] += r * n_words
+            d["res_offset"][sl] += r * n_words
+        d_descs = torch.from_numpy(d.view(np.uint8).reshape(-1)).to(dev)
+        d_words = torch.cat([words.repeat(tile), torch.zeros(8, dtype=words.dtype, device=dev)])
+        n_sub = d.size
+        res = torch.empty(n_sub * FRAME, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def run():
+            _lib.check(L.selab200_rice_decode_frames_device(d_descs.data_ptr(), n_frames * tile, CHANNELS, d_words.data_ptr(),
+                                                            n_words * tile, res.data_ptr(), status.data_ptr(), C.c_void_p(stream)))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize(dev)
+        reps = 10 if tile == 1 else 4
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(reps):
+            run()
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        flagged = C.c_uint32(0)
+        _lib.check(L.selab200_rice_decode_flagged(C.addressof(flagged)))
+        alg = res_words * tile * 4 + n_sub * FRAME * 4
+        out["streams_%d" % n_sub] = {
+            "streams": n_sub, "ms": ms, "gsamples_s": n_sub * FRAME / ms / 1e6, "achieved": alg / ms / 1e6, "unit": "GB/s",
+            "peak": peak, "frac": alg / ms / 1e6 / peak, "algorithmic_bytes": alg, "status": int(status.item()),
+            "streams_redone_by_general_parser": int(flagged.value)}
+        del d_descs, d_words, res
+    return out
+
+
+def pcie_probe(dev, nbytes=128 << 20):
+    """Pinned-memory copy rates of this box (they differ by 2x between boxes; the e2e number is PCIe bound)."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        res[name] = 3 * nbytes / a.elapsed_time(b) / 1e6
+    return res
+
+
+def sharded_block(args, rank, world, dev, dist):
+    """BASELINE configs[3] and [4] on the N GPUs of this run.
+      config4: ONE 48 kHz 8-channel file coded by all ranks: PCM scattered from rank 0 over NCCL, every rank
+               encodes its contiguous block of frames, coded subframes gathered on rank 0 (offsets re-based);
+               then the reverse for decode.  Checked against rank 0 coding the whole file alone.
+      config5: a batch of independent 3-minute stereo files, 1024 / N per rank, coded file by file."""
+    import torch
+    from sela_b200 import distributed as sd, synth
+    from sela_b200.device import DeviceCodec
+    out = {}
+    # ---------------- config 4 ----------------
+    ch, rate = 8, 48000
+    base_min, reps = 3, 20 if not args.sharded_minutes else max(1, args.sharded_minutes // 3)
+    n_base = (rate * 60 * base_min) // FRAME
+    n_frames = n_base * reps
+    per = FRAME * ch
+    if rank == 0:
+        base = torch.from_numpy(synth.sine_noise(rate, ch, n_frames=n_base, seed=2).reshape(-1))
+        pcm_dev = torch.empty(n_frames * per, dtype=torch.int16, device=dev)
+        t0 = time.perf_counter()
+        base_dev = base.pin_memory().to(dev, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        h2d_s = time.perf_counter() - t0
+        for r in range(reps):
+            pcm_dev[r * n_base * per:(r + 1) * n_base * per].copy_(base_dev)
+        del base_dev
+    else:
+        pcm_dev, h2d_s = None, 0.0
+    if dist:
+        dist.barrier()
+    if dist:
+        (d_all, w_all), t_enc = sd.encode_sharded_device(pcm_dev, n_frames, ch, root=0)
+        (d_all2, w_all2), t_enc2 = sd.encode_sharded_device(pcm_dev, n_frames, ch, root=0)   # second pass: warm
+        pcm_back, t_dec = sd.decode_sharded_device(d_all2, w_all2, n_frames, ch, root=0)
+    else:
+        t_enc2 = t_dec = None
+    c4 = {"workload": "48 kHz 16-bit 8-channel, %d min (%d x the %d-minute seed-2 synthetic), one file across %d GPU(s)" % (
+        base_min * reps, reps, base_min, world), "frames": n_frames, "samples": n_frames * per}
+    if rank == 0:
+        single = DeviceCodec(n_frames, ch, device=dev.index)
+        single.encode(pcm_dev)
+        torch.cuda.synchronize(dev)
+        (_, ms1) = sd._timed(lambda: single.encode(pcm_dev), dev)
+        single.check_status()
+        nw1 = int(single.words_used.item())
+        out1 = torch.empty_like(pcm_dev)
+        single.decode(out1, nw1)
+        torch.cuda.synchronize(dev)
+        (_, ms1d) = sd._timed(lambda: single.decode(out1, nw1), dev)
+        single.check_status()
+        c4["single_gpu"] = {"encode_ms": ms1, "decode_ms": ms1d, "encode_msamples_s": n_frames * per / ms1 / 1e3,
+                            "decode_msamples_s": n_frames * per / ms1d / 1e3, "words": nw1,
+                            "decode_equals_source_samples": int((out1 == pcm_dev).sum().item()), "samples": n_frames * per}
+        if dist:
+            same = bool(torch.equal(d_all2, single.descs)) and w_all2.numel() == nw1 and bool(torch.equal(w_all2, single.words[:nw1]))
+            c4["bytes_identical_to_single_gpu"] = same
+            c4["decode_identical_to_single_gpu"] = bool(torch.equal(pcm_back, out1))
+        c4["root_upload_gbs"] = base.numel() * 2 / h2d_s / 1e9
+        del single, out1
+    if dist:
+        # max over ranks of every phase, wall time of the whole sharded call = sum of the phase maxima
+        keys_e, keys_d = ("scatter_ms", "encode_ms", "gather_ms"), ("scatter_ms", "decode_ms", "gather_ms")
+        t = torch.tensor([t_enc2[k] for k in keys_e] + [t_dec[k] for k in keys_d], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = t.tolist()
+        c4["nccl_encode"] = dict(zip(keys_e, v[:3]))
+        c4["nccl_decode"] = dict(zip(keys_d, v[3:]))
+        c4["nccl_encode"]["msamples_s"] = n_frames * per / sum(v[:3]) / 1e3
+        c4["nccl_encode"]["msamples_s_kernels_only"] = n_frames * per / v[1] / 1e3
+        c4["nccl_decode"]["msamples_s"] = n_frames * per / sum(v[3:]) / 1e3
+        c4["nccl_decode"]["msamples_s_kernels_only"] = n_frames * per / v[4] / 1e3
+        c4["note"] = ("scatter/gather move PCM (2 B/sample) and coded words between HBMs over NVLink; rank 0's own "
+                      "PCIe upload/download is not in these times")
+    out["config4"] = c4
+    del pcm_dev
+    torch.cuda.empty_cache()
+    # ---------------- config 5 ----------------
+    files_total, distinct = 1024, 8
+    file_frames = (44100 * 180) // FRAME                       # 3 875 whole frames of a 3-minute file (the tail is dropped)
+    fs = FRAME * 2 * file_frames
+    bank = torch.empty(distinct * fs, dtype=torch.int16, device=dev)
+    if rank == 0:
+        for i in range(distinct):
+            bank[i * fs:(i + 1) * fs].copy_(torch.from_numpy(synth.sine_noise(44100, 2, n_frames=file_frames, seed=i).reshape(-1)))
+    if dist:
+        dist.broadcast(bank, 0)
+    mine = files_total // world + (1 if rank < files_total % world else 0)
+    codec = DeviceCodec(file_frames, 2, device=dev.index)
+    outp = torch.empty(fs, dtype=torch.int16, device=dev)
+
+    def code_file(i):
+        pcm = bank[(i % distinct) * fs:(i % distinct + 1) * fs]
+        codec.encode(pcm)
+        return pcm
+    nw = []
+    for i in range(distinct):                                     # warm-up + the word counts the decoder needs
+        code_file(i)
+        torch.cuda.synchronize(dev)
+        nw.append(int(codec.words_used.item()))
+    ok = True
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for i in range(mine):
+        code_file(i)
+    ev[1].record()
+    for i in range(mine):
+        code_file(i)                                              # (the decoder reads what the encoder just wrote)
+        codec.decode(outp, nw[i % distinct])
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    codec.check_status()
+    ok = bool(torch.equal(outp, bank[((mine - 1) % distinct) * fs:((mine - 1) % distinct + 1) * fs])) if mine else True
+    enc_ms = ev[0].elapsed_time(ev[1])
+    dec_ms = ev[1].elapsed_time(ev[2]) - enc_ms                   # second loop = encode + decode
+    t = torch.tensor([enc_ms, dec_ms, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    enc_ms, dec_ms, bad = t.tolist()
+    total = files_total * fs
+    out["config5"] = {
+        "workload": "1024 independent 3-minute 44.1 kHz stereo files (%d distinct synthetic files, seeds 0..%d, reused), %s per rank, "
+                    "one encode and one decode call per file, device resident" % (distinct, distinct - 1, "%d or %d" % (files_total // world, -(-files_total // world)) if files_total % world else str(files_total // world)),
+        "files": files_total, "frames_per_file": file_frames, "samples": total,
+        "encode_ms": enc_ms, "decode_ms": dec_ms, "encode_msamples_s": total / enc_ms / 1e3, "decode_msamples_s": total / dec_ms / 1e3,
+        "encode_decode_msamples_s": total / (enc_ms + dec_ms) / 1e3, "round_trip_bit_exact": bad == 0.0}
+    return out
 
 
 _REAL_STDOUT = []
@@ -155,27 +384,54 @@ def cpu_reference_leg(pcm, target_seconds=8.0):
 
 
 def run_reference(args, rank, world):
+    """The reference's own multithreaded CPU coder (sela::Encoder/Decoder::processFrames of oracle/_ref, or the
+    plain-C port when the reference was not compiled) on the host cores.  A step = encode + decode of a
+    BOUNDED SAMPLE of the workload (the first frames of the file; frames are independent, so the rate is the
+    whole file's), sized by a probe so that warm-up + steps end within minutes on any box."""
     if rank != 0:
         return
+    import oracle_lib as ol
+    O = ol.best()
     pcm = make_pcm(1)
-    for _ in range(args.warmup):
-        pass  # the CPU path has no warm-up state worth modelling; passes below are all timed
-    passes = []
-    info = None
-    for _ in range(max(1, min(args.steps, 3))):
-        info, _ = cpu_reference_leg(pcm, target_seconds=6.0)
-        passes.append(info["value"])
-    info["value"] = statistics.median(passes)
-    n_samples = (pcm.shape[0] // FRAME) * FRAME * CHANNELS
+    n_frames = pcm.shape[0] // FRAME
+    n_samples_file = n_frames * FRAME * CHANNELS
+    probe = min(n_frames, 512)
+    t_probe = O.time_encode(pcm[:probe * FRAME], CHANNELS)
+    d_p, w_p = O.encode_frames(pcm[:probe * FRAME], CHANNELS)
+    t_probe += O.time_decode(d_p, w_p, CHANNELS)
+    rate = probe / max(t_probe, 1e-6)                     # frames per second, encode + decode
+    budget = 90.0 / max(1, args.steps + args.warmup)      # seconds per step
+    sample_frames = int(max(min(probe, n_frames), min(n_frames, rate * min(budget, 2.0))))
+    sample = pcm[:sample_frames * FRAME]
+    descs, words = O.encode_frames(sample, CHANNELS)
+    n_samples = sample_frames * FRAME * CHANNELS
+    times = []
+    for i in range(args.warmup + args.steps):
+        te = O.time_encode(sample, CHANNELS)
+        td = O.time_decode(descs, words, CHANNELS)
+        if i >= args.warmup:
+            times.append((te, td))
+    tot = [a + b for a, b in times]
+    mean_s = statistics.fmean(tot)
+    value = n_samples / mean_s / 1e6
+    info = {
+        "value": value, "unit": "MSamples/s", "cores": O.cores, "threads": O.cores, "kind": O.kind,
+        "sample": "each step: first %d of %d frames (%.1f s of audio) encoded then decoded; timed: %s" % (
+            sample_frames, n_frames, sample_frames * FRAME / SAMPLE_RATE,
+            "sela::Encoder/Decoder::processFrames only" if O.kind == "reference" else "oracle port batch calls"),
+        "encode_msamples_s": n_samples / statistics.fmean(t[0] for t in times) / 1e6,
+        "decode_msamples_s": n_samples / statistics.fmean(t[1] for t in times) / 1e6,
+        "step_ms_min": min(tot) * 1e3, "step_ms_max": max(tot) * 1e3,
+        "whole_file_equivalent_ms": n_samples_file / (value * 1e6) * 1e3,
+    }
     line = {
-        "impl": "reference", "metric": METRIC, "value": info["value"], "unit": "MSamples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": n_samples / (info["value"] * 1e6) * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64+int64 (CPU)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: each step codes a bounded sample of the workload "
-                   "and scales linearly (frames are independent); ms_per_step is the whole-file equivalent"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
+        "config": workload_config(n_frames, n_samples_file),
+        "step_sample_frames": sample_frames,
         "cpu_baseline": info,
-        "e2e": {"value": info["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit_line(line)
@@ -300,9 +556,32 @@ def run_ours(args, rank, world, local_rank):
     value = total_samples * args.steps / (total_ms_max * 1e-3) / 1e6
     e2e_value = total_samples / (e2e_ms_max * 1e-3) / 1e6
 
+    # ---------------- the Rice-decode kernel on its own; PCIe rates of this box; the sharded configs ----------------
+    peak, peak_src = measured_peak_hbm()
+    rice = pcie = None
     if rank == 0:
-        peak, peak_src = measured_peak_hbm()
+        try:
+            rice = rice_decode_roofline(codec, n_frames, n_words, dev, peak)
+        except Exception as e:                      # never lose the headline to a side measurement
+            rice = {"error": repr(e)[:300]}
+        try:
+            pcie = pcie_probe(dev)
+        except Exception as e:
+            pcie = {"error": repr(e)[:300]}
+    sharded = None
+    if not args.no_sharded:
+        del pcm, out
+        torch.cuda.empty_cache()
+        try:
+            sharded = sharded_block(args, rank, world, dev, dist)
+        except Exception as e:
+            sharded = {"error": repr(e)[:400]}
+            if dist:
+                raise                                # a rank that drops out of a collective must not hang the others silently
+
+    if rank == 0:
         desc_bytes = n_frames * CHANNELS * 32
+        prof, stale = measured_profile("k_encode_units<stereo>")
         enc_bytes = n_samples * 2 + n_words * 4 + desc_bytes              # algorithmic: PCM in, words + descs out
         achieved = enc_bytes / (enc_ms * 1e-3) / 1e9
         line = {
@@ -310,26 +589,36 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": n_frames, "samples_per_gpu": n_samples,
-                       "l2": "no flush needed: per step the kernels stream 106 MB PCM + %d MB words + "
-                             "%d MB residue workspace, larger than the 126 MB L2" % (
-                                 n_words * 4 >> 20, n_frames * CHANNELS * FRAME * 4 >> 20),
-                       "bits_per_sample": n_words * 32 / n_samples},
+            "config": workload_config(n_frames, n_samples),
+            "bits_per_sample": n_words * 32 / n_samples,
             "encode_msamples_s": n_samples / (enc_ms * 1e-3) / 1e6,
             "decode_msamples_s": n_samples / (dec_ms * 1e-3) / 1e6,
             "encode_ms": enc_ms, "decode_ms": dec_ms,
             "round_trip_bit_exact": round_trip_ok and e2e_ok,
             "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max, "steps": e2e_steps,
-                    "encode_ms": split[0] / e2e_steps * 1e3, "decode_ms": split[1] / e2e_steps * 1e3},
+                    "encode_ms": split[0] / e2e_steps * 1e3, "decode_ms": split[1] / e2e_steps * 1e3,
+                    "pcie_probe": pcie,
+                    "copy_floor_ms": None if not pcie or "error" in pcie else
+                    (h2d / (pcie["h2d_gbs"] * 1e6) + d2h / (pcie["d2h_gbs"] * 1e6)) / 2,
+                    "note": "copy_floor_ms = (H2D bytes / probed H2D rate + D2H bytes / probed D2H rate) / 2: the two "
+                            "directions overlap, so a step cannot be faster than about this"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("k_encode_units<stereo>"), "peak_source": peak_src,
+                         "traffic": (prof or {}).get("traffic"), "traffic_stale": stale, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": enc_bytes,
-                         "note": "FP64-latency / instruction-issue bound, not HBM bound (DESIGN.md 4); "
-                                 "traffic = dram read+write per launch from profiles/traffic.json (ncu)"},
+                         "compute": {"pipe": "fp64", "busy_frac": (prof or {}).get("fp64_busy_frac"),
+                                     "issue_active_frac": (prof or {}).get("issue_active_frac"),
+                                     "fp64_ops_per_launch": n_frames * 3 * (2 * FRAME * 101 + 2 * FRAME),
+                                     "note": "busy_frac / issue_active_frac from the committed ncu capture (profiles/traffic.json); "
+                                             "ops = sequentially rounded multiplies and adds of the 101-lag autocorrelation + mean, 3 units per stereo frame"},
+                         "note": "FP64-latency / instruction-issue bound, not HBM bound (DESIGN.md 4); traffic = dram "
+                                 "read+write per launch from profiles/traffic.json (ncu), traffic_stale = kernel sources "
+                                 "changed since that capture"},
+            "roofline_rice_decode": rice,
+            "sharded": sharded,
         }
         if world == 1 and not args.no_cpu:
             info, (sf, d_ref, w_ref) = cpu_reference_leg(pcm_np)
@@ -352,6 +641,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the configs[3]/[4] block (profiling runs)")
+    ap.add_argument("--sharded-minutes", type=int, default=0, help="length of the config-4 file (default 60)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -339,8 +339,12 @@ int rice_split_log2(size_t n_sub)
             l++;
         return l;
     }
+    // Measured on B200 (profiles/r02_rice_decode_roofline.json): from about 20 000 streams up one lane per stream
+    // (S = 1) through k_rice_decode_vs is fastest -- the two split passes cost more than the extra warps bring
+    // once every SM has a few warps of its own; below that the machine is starved and cutting the streams
+    // wins.
     int l = 0;
-    while (l < 4 && (n_sub << l) < (size_t)180000)
+    while (l < 4 && (n_sub << l) < (size_t)20000)
         l++;
     return l;
 }
@@ -348,12 +352,21 @@ int rice_split_log2(size_t n_sub)
 template <int LOG2S>
 int launch_split_index(const RiceVsParams &q, size_t n_sub, cudaStream_t stream)
 {
-    constexpr int W = 32 >> LOG2S, kWarps = 2;
-    const size_t smem = rice_split_smem_bytes(LOG2S, q.cap_words, kWarps);
-    if (int rc = set_smem(k_rice_split_index<LOG2S>, smem))
-        return rc;
-    const unsigned blocks = (unsigned)((n_sub + W * kWarps - 1) / (W * kWarps));
-    k_rice_split_index<LOG2S><<<blocks, 32 * kWarps, smem, stream>>>(q);
+    const unsigned blocks = (unsigned)(((n_sub << LOG2S) + 32 * kVsWarps - 1) / (32 * kVsWarps));
+    int geom = 1;
+    if (const char *env = std::getenv("SELAB200_RICE_GEOM_A"))
+        geom = std::atoi(env);
+    if (geom == 1) {
+        constexpr size_t smem = split_smem_bytes<32>();
+        if (int rc = set_smem(k_rice_split_index<LOG2S, 32, 16>, smem))
+            return rc;
+        k_rice_split_index<LOG2S, 32, 16><<<blocks, 32 * kVsWarps, smem, stream>>>(q);
+    } else {
+        constexpr size_t smem = split_smem_bytes<64>();
+        if (int rc = set_smem(k_rice_split_index<LOG2S, 64, 16>, smem))
+            return rc;
+        k_rice_split_index<LOG2S, 64, 16><<<blocks, 32 * kVsWarps, smem, stream>>>(q);
+    }
     return launch_check("k_rice_split_index");
 }
 
@@ -373,12 +386,6 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
     q.table = static_cast<uint32_t *>(aux);
     q.flags = q.table + n_sub * 15;
     q.status = p.status;
-    q.cap_words = 1152;
-    if (const char *env = std::getenv("SELAB200_RICE_SPLIT_CAP")) {
-        const long v = std::atol(env);
-        if (v >= 64 && v <= 8192)
-            q.cap_words = (uint32_t)(v & ~3l);
-    }
     int rc = 0;
     switch (log2s) {
     case 0: CUDA_TRY(cudaMemsetAsync(q.flags, 0, n_sub * 4, stream)); break;
@@ -389,10 +396,28 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
     }
     if (rc)
         return rc;
-    if (int rc2 = set_smem(k_rice_decode_vs, kVsSmemBytes))
-        return rc2;
     const size_t n_vs = n_sub << log2s;
-    k_rice_decode_vs<<<(unsigned)((n_vs + 32 * kVsWarps - 1) / (32 * kVsWarps)), 32 * kVsWarps, kVsSmemBytes, stream>>>(q, log2s);
+    const unsigned vs_blocks = (unsigned)((n_vs + 32 * kVsWarps - 1) / (32 * kVsWarps));
+    // geometry: 0 = deep ring, full-line stores (fewest instructions); 1 = half the shared memory, twice the warps
+    int geom = 0;
+    if (const char *env = std::getenv("SELAB200_RICE_GEOM"))
+        geom = std::atoi(env);
+    if (geom == 1) {
+        constexpr size_t smem = vs_smem_bytes<32, 16>();
+        if (int rc2 = set_smem(k_rice_decode_vs<32, 16, 16>, smem))
+            return rc2;
+        k_rice_decode_vs<32, 16, 16><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom == 2) {
+        constexpr size_t smem = vs_smem_bytes<32, 32>();
+        if (int rc2 = set_smem(k_rice_decode_vs<32, 16, 32>, smem))
+            return rc2;
+        k_rice_decode_vs<32, 16, 32><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else {
+        constexpr size_t smem = vs_smem_bytes<64, 32>();
+        if (int rc2 = set_smem(k_rice_decode_vs<64, 16, 32>, smem))
+            return rc2;
+        k_rice_decode_vs<64, 16, 32><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    }
     if (int rc2 = launch_check("k_rice_decode_vs"))
         return rc2;
     DecodeParams pf = p; // whatever was flagged: the general lane-per-stream parser decodes it again

@@ -15,10 +15,13 @@
 //                           the next lane's boundaries are the true ones.  A prefix sum of the
 //                           per-lane symbol counts then names the lane (and, through sparse
 //                           checkpoints, the bit) where symbol t*2048/S begins.
-//   k_rice_decode_vs        one lane per virtual stream: a register bit window over a private
-//                           shared-memory ring that the lane tops up with cp.async (no dependent
-//                           shared-memory load on the per-symbol chain), values staged in a shared
-//                           tile and written as whole 128-byte lines.
+//   k_rice_decode_vs        one lane per virtual stream, decoding values.
+//
+// Both kernels read the stream the same way: every lane owns a small ring in shared memory that it tops
+// up itself with 16-byte cp.async copies (no cooperation, no registers held across the load latency),
+// and parses from a three-word register window, so that no shared-memory load sits on the
+// symbol-to-symbol dependency chain.  The decoder stages its values in a shared tile and writes them as
+// whole row segments (128-byte lines) instead of one 16-byte store per lane.
 //
 // Nothing is taken on trust: part l must end exactly where the table says part l+1 begins (part 0
 // starts at bit 0, so by induction every part is the sequential parse); a stream that fails that
@@ -32,6 +35,7 @@
 namespace selab200 {
 
 constexpr uint32_t kNoSplit = 0xffffffffu;
+constexpr int kVsWarps = 4;
 
 struct RiceVsParams {
     const selab200_subframe_desc *descs;
@@ -42,7 +46,6 @@ struct RiceVsParams {
     uint32_t *table;   // [n_sub][S-1]: bit position (from the stream's first bit) of symbol t*2048/S
     uint32_t *flags;   // [n_sub]: 1 = the general kernel must decode this stream
     int32_t *status;
-    uint32_t cap_words; // k_rice_split_index: staged words per stream
 };
 
 __device__ __forceinline__ bool rice_desc_ok(const selab200_subframe_desc &d, uint32_t channels, unsigned long long n_words)
@@ -53,139 +56,374 @@ __device__ __forceinline__ bool rice_desc_ok(const selab200_subframe_desc &d, ui
            !(d.subframe_type == 1 && d.parent_channel == d.channel);
 }
 
+// Position of the highest set bit, 0xffffffff for zero: the raw FLO, without the 31 - x of __clz.
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x)
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// convertUnsignedToSigned (src/rice/rice_decoder.cpp:46-52) in three instructions: the sign is bit 0 of u,
+// sign-extended by a one-bit signed field extract.
+__device__ __forceinline__ int32_t unzigzag3(uint32_t u)
+{
+    int32_t s;
+    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(s) : "r"(u));
+    return (int32_t)(u >> 1) ^ s;
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// ------------------------------------------------------------------ the lane's ring --
+//
+// RING words in one row of shared memory, word w of the stream (counted from its 16-byte aligned base) at
+// byte ((4w + rot) & (4*RING - 1)) of the row; rot = 16 * lane spreads the lanes over the banks.  Rows are
+// 4*RING-aligned in the shared window: addresses are formed with OR.
+template <int RING>
+struct VsRing {
+    static constexpr uint32_t kMask = RING * 4 - 1;
+    uint32_t row, rot;  // shared-space byte address of the row; rotation
+    const uint4 *gvec;  // the stream from its 16-byte aligned base
+    int total_bytes;    // bytes from gvec to the end of the stream; everything behind reads as zero
+    __device__ __forceinline__ uint32_t word_addr(uint32_t w) const { return row | ((4 * w + rot) & kMask); }
+    __device__ __forceinline__ uint32_t word(uint32_t w) const { return lds_u32(word_addr(w)); }
+    __device__ __forceinline__ void issue(uint32_t fv) const // vector fv: words [4fv, 4fv+4)
+    {
+        const uint32_t off = 16 * fv;
+        const uint32_t dst = row | ((off + rot) & kMask);
+        if ((int)(off + 16) <= total_bytes) { // the common case: a whole vector of the stream
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + off) : "memory");
+        } else { // the ragged end, and zeros behind it
+            const int rem = total_bytes - (int)off;
+            const uint32_t sz = rem <= 0 ? 0u : (uint32_t)rem;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + (sz ? off : 0u)), "r"(sz) : "memory");
+        }
+    }
+    // The value parser wants the stream MSB first (a leading-zero count finds the terminator, the payload
+    // reads as a number); BREV costs three issue slots on sm_100a, so the words are reversed once, in place,
+    // when their vector has landed -- not once per symbol.
+    __device__ __forceinline__ void reverse(uint32_t v) const
+    {
+        const uint32_t a = row | ((16 * v + rot) & kMask);
+        uint32_t x, y, z, w;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
+        x = __brev(x), y = __brev(y), z = __brev(z), w = __brev(w);
+        asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x), "r"(y), "r"(z), "r"(w), "r"(a) : "memory");
+    }
+    // vectors [lo, hi): two loads in flight before the first BREV
+    __device__ __forceinline__ void reverse_range(uint32_t lo, uint32_t hi) const
+    {
+        for (; lo + 1 < hi; lo += 2) {
+            const uint32_t a = row | ((16 * lo + rot) & kMask), b = row | ((16 * lo + 16 + rot) & kMask);
+            uint32_t x0, y0, z0, w0, x1, y1, z1, w1;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(z0), "=r"(w0) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x1), "=r"(y1), "=r"(z1), "=r"(w1) : "r"(b));
+            x0 = __brev(x0), y0 = __brev(y0), z0 = __brev(z0), w0 = __brev(w0);
+            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x0), "r"(y0), "r"(z0), "r"(w0), "r"(a) : "memory");
+            x1 = __brev(x1), y1 = __brev(y1), z1 = __brev(z1), w1 = __brev(w1);
+            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x1), "r"(y1), "r"(z1), "r"(w1), "r"(b) : "memory");
+        }
+        if (lo < hi)
+            reverse(lo);
+    }
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The streaming state of a lane: a window of three words in registers (r0 = word wb - 1 holds the current
+// bit, r1, and r2 loaded one word ahead of its first use) over the ring.  ROUND symbols of at most 32 bits
+// are parsed between two boundaries; at a boundary the ring is topped up as far as the words still needed
+// allow, and the copies issued at the previous boundary are retired (and, for the value parser, reversed).
+// A round reads at most ROUND + 2 words past r1.  With RING >= 2 * ROUND + 16 what landed a boundary ago
+// always covers that; a smaller ring (half the shared memory, twice the warps per SM) covers it for
+// ordinary streams and otherwise waits for the copies just issued (RING >= ROUND + 16 suffices then).
+template <int RING, int ROUND, bool REVERSED>
+struct VsStream {
+    static_assert(RING >= ROUND + 16 && (RING & (RING - 1)) == 0, "ring too small for the round");
+    VsRing<RING> rg;
+    uint32_t pos;         // current bit, counted from the aligned base
+    uint32_t r0, r1, r2;  // window
+    uint32_t wa;          // running byte offset (rotated) of r2's word
+    uint32_t fv, rv;      // next vector to request / first vector not yet landed (and reversed)
+    uint32_t cv_next;     // vectors below cv_next have been requested by the previous boundary
+    uint32_t ce;          // words below ce have landed (and are reversed)
+
+    __device__ __forceinline__ uint32_t wb() const { return (pos >> 5) + 1; }
+    __device__ __forceinline__ void load_window()
+    {
+        const uint32_t w = wb();
+        r0 = rg.word(w - 1);
+        r1 = rg.word(w);
+        r2 = rg.word(w + 1);
+        wa = 4 * (w + 1) + rg.rot;
+    }
+    __device__ __forceinline__ void retire(uint32_t upto) // vectors below `upto` have landed
+    {
+        if (upto > rv) {
+            if (REVERSED)
+                rg.reverse_range(rv, upto);
+            rv = upto;
+            ce = 4 * upto;
+        }
+    }
+    // (Re)start at bit p.  Every earlier copy of this lane must have landed.
+    __device__ __forceinline__ void prime(uint32_t p)
+    {
+        pos = p;
+        const uint32_t w = wb();
+        fv = rv = (w - 1) >> 2;
+        const uint32_t first = (w + ROUND + 2) >> 2; // last vector the first round can touch
+        while (fv <= first) {
+            rg.issue(fv);
+            fv++;
+        }
+        cp_async_commit();
+        const uint32_t landed = fv;
+        const uint32_t lim = (w + RING - 5) >> 2; // vector v overwrites words [4v - RING, 4v - RING + 3]; below w - 1 all is dead
+        while (fv <= lim) {
+            rg.issue(fv);
+            fv++;
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        ce = 4 * rv;
+        retire(landed);
+        cv_next = fv;
+        load_window();
+    }
+    __device__ __forceinline__ void boundary()
+    {
+        const uint32_t w = wb();
+        const uint32_t lim = (w + RING - 5) >> 2;
+        while (fv <= lim) {
+            rg.issue(fv);
+            fv++;
+        }
+        cp_async_commit();
+        cp_async_wait<1>(); // everything but the group just committed has landed
+        retire(cv_next);
+        cv_next = fv;
+        if (RING < 2 * ROUND + 16 && ce < w + ROUND + 3) { // a dense stretch: the round may outrun what has landed
+            cp_async_wait<0>();
+            retire(fv);
+        }
+    }
+    // one word further (the parser crossed a 32-bit boundary)
+    __device__ __forceinline__ void advance()
+    {
+        r0 = r1;
+        r1 = r2;
+        wa += 4;
+        r2 = lds_u32(rg.row | (wa & VsRing<RING>::kMask));
+    }
+};
+
 // ------------------------------------------------------------------ split index --
+//
+// No payload is read here, so the words stay as they lie in memory (stream bit b = bit b%32 of word b/32):
+// the terminator of a symbol is the lowest zero of the window, isolated with ~w & (w + 1); no bit reversal.
 
 constexpr int kCpDense = 16;             // checkpoints at symbols 0, 4, .., 60 of a lane's own parse,
-constexpr int kCpMax = kCpDense + 66;    // then at 64, 96, ..: boundary positions relative to the chunk start
+constexpr int kCpMax = kCpDense + 32;    // then at 64, 96, ..: boundary positions relative to the chunk start
 __device__ __forceinline__ uint32_t cp_symbol(uint32_t i) { return i < kCpDense ? 4 * i : 64 + 32 * (i - kCpDense); }
 __device__ __forceinline__ uint32_t cp_index(uint32_t j) { return j < 64 ? j >> 2 : kCpDense + ((j - 64) >> 5); }
+__device__ __forceinline__ uint32_t cp_count(uint32_t n) { return n == 0 ? 0u : cp_index(n - 1) + 1; } // checkpoints among symbols 0..n-1
 
-// Position of the symbol boundary after the one at bit q.  sw: the stream's words, bit-reversed
-// (stream bit b = bit 31 - b%32 of sw[b/32]), zero beyond total_bits.  Any run length.
-__device__ __noinline__ uint32_t rice_next_boundary(const uint32_t *sw, uint32_t total_bits, uint32_t q, uint32_t kp1)
+// Random access for the short walks (merge search, table look-up, the tail of a chunk, long symbols):
+// RING consecutive words at a time, fetched on demand.  Every earlier copy of the lane must have landed.
+template <int RING>
+struct VsReader {
+    VsRing<RING> rg;
+    uint32_t base_w, end_w;
+};
+template <int RING>
+__device__ __noinline__ uint32_t reader_next_boundary(VsReader<RING> *rd, uint32_t total_bits, uint32_t q, uint32_t kp1)
 {
     while (q < total_bits) {
         const uint32_t w = q >> 5;
-        const uint32_t c = __clz(~__funnelshift_l(sw[w + 1], sw[w], q));
-        q += c;
+        if (w < rd->base_w || w + 1 >= rd->end_w) {
+            const uint32_t fv0 = w >> 2;
+            for (uint32_t i = 0; i < RING / 4; i++)
+                rd->rg.issue(fv0 + i);
+            cp_async_commit();
+            cp_async_wait<0>();
+            rd->base_w = 4 * fv0;
+            rd->end_w = rd->base_w + RING;
+        }
+        const uint32_t win = __funnelshift_r(rd->rg.word(w), rd->rg.word(w + 1), q);
+        const uint32_t c = bfind_u32(~win & (win + 1)); // trailing ones; 0xffffffff: 32 or more
         if (c < 32)
-            return q + kp1;
+            return q + c + kp1;
+        q += 32;
     }
     return total_bits + kp1; // ran off the end: the zero padding terminates the run
 }
 
-template <int LOG2S>
-__global__ void __launch_bounds__(128) k_rice_split_index(RiceVsParams p)
+template <int LOG2S, int RING, int ROUND>
+__global__ void __launch_bounds__(32 * kVsWarps) k_rice_split_index(RiceVsParams p)
 {
-    constexpr int S = 1 << LOG2S, W = 32 >> LOG2S; // lanes per stream, streams per warp
+    static_assert(ROUND % 4 == 0 && 64 % ROUND == 0, "geometry");
+    constexpr int S = 1 << LOG2S;
     constexpr uint32_t kPart = kFrame >> LOG2S;
     extern __shared__ __align__(16) unsigned char split_smem[];
-    const uint32_t pitch = p.cap_words + 8; // + zero words behind the last one
     const int lane = lane_id(), warp = warp_id();
-    uint32_t *stage = reinterpret_cast<uint32_t *>(split_smem) + (size_t)warp * W * pitch;
-    uint16_t *cps = reinterpret_cast<uint16_t *>(split_smem + (size_t)(blockDim.x >> 5) * W * pitch * 4) + (size_t)warp * kCpMax * 32;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(split_smem);
+    const uint32_t pad = (RING * 4 - (smem0 & (RING * 4 - 1))) & (RING * 4 - 1);
+    uint16_t *cps = reinterpret_cast<uint16_t *>(split_smem + pad + kVsWarps * 32 * RING * 4) + (size_t)warp * kCpMax * 32;
 
-    const uint32_t g = lane >> LOG2S, l = lane & (S - 1), gb = lane & ~(S - 1);
-    const uint32_t st = (blockIdx.x * (blockDim.x >> 5) + warp) * W + g;
+    const uint32_t l = lane & (S - 1), gb = lane & ~(S - 1);
+    const uint32_t st = ((blockIdx.x * kVsWarps + warp) * 32 + lane) >> LOG2S;
     const bool exists = st < p.n_sub;
     selab200_subframe_desc d;
     memset(&d, 0, sizeof d);
     if (exists)
         d = p.descs[st];
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p.words + d.res_offset);
+    // splittable: well-formed and every lane gets at least four words
+    const bool ok = exists && rice_desc_ok(d, p.channels, p.n_words) && d.res_words >= 4u * S;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p.words + (ok ? d.res_offset : 0));
     const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
-    const uint4 *gvec = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
-    const uint32_t total = (uint32_t)d.res_words + skip; // words from the aligned base
-    const uint32_t kp1 = (uint32_t)d.res_rice_param + 1;
-    // splittable: well-formed, fits the staging area, every lane gets at least four words
-    bool ok = exists && rice_desc_ok(d, p.channels, p.n_words) && total <= p.cap_words && d.res_words >= 4u * S;
+    const uint32_t total = ok ? (uint32_t)d.res_words + skip : 0u; // words from the aligned base
+    const uint32_t k = ok ? d.res_rice_param : 0u, kp1 = k + 1;
 
-    // ---- stage the W streams of this warp, bit-reversed, zero behind the end ----
-    uint32_t *sw = stage + (size_t)g * pitch;
-#pragma unroll 1
-    for (int t = 0; t < W; t++) {
-        const int src_lane = t << LOG2S;
-        const bool ok_t = __shfl_sync(kFull, ok, src_lane);
-        const uint32_t total_t = __shfl_sync(kFull, total, src_lane);
-        const unsigned long long gv = __shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(gvec), src_lane);
-        if (!ok_t)
-            continue;
-        const uint4 *gp = reinterpret_cast<const uint4 *>((uintptr_t)gv);
-        uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)t * pitch);
-        const uint32_t nvec = (total_t + 8 + 3) >> 2; // through the zero words
-        for (uint32_t i = lane; i < nvec; i += 32) {
-            uint4 v = 4 * i < total_t ? __ldg(gp + i) : make_uint4(0, 0, 0, 0);
-            v.x = 4 * i + 0 < total_t ? __brev(v.x) : 0u;
-            v.y = 4 * i + 1 < total_t ? __brev(v.y) : 0u;
-            v.z = 4 * i + 2 < total_t ? __brev(v.z) : 0u;
-            v.w = 4 * i + 3 < total_t ? __brev(v.w) : 0u;
-            if (4 * i + 3 < (uint32_t)pitch)
-                dst[i] = v;
-        }
-    }
-    __syncwarp();
+    using Stream = VsStream<RING, ROUND, false>;
+    Stream s;
+    s.rg.row = smem0 + pad + (uint32_t)(warp * 32 + lane) * (RING * 4);
+    s.rg.rot = (16u * lane) & (RING * 4 - 1);
+    s.rg.gvec = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    s.rg.total_bytes = (int)(total * 4);
+    VsReader<RING> rd;
+    rd.rg = s.rg;
+    rd.base_w = rd.end_w = 0;
 
     // ---- phase 1: every lane parses the boundaries of its own chunk of bits ----
     const uint32_t total_bits = total * 32;
-    const uint32_t cw = total >> LOG2S;                                  // words per chunk (>= 4); the last lane takes the rest
-    const uint32_t cstart = l == 0 ? skip * 32 : l * cw * 32;           // lane 0 starts at the stream's first bit: a true boundary
+    const uint32_t cw = total >> LOG2S;                                // words per chunk (>= 4); the last lane takes the rest
+    const uint32_t cstart = l == 0 ? skip * 32 : l * cw * 32;         // lane 0 starts at the stream's first bit: a true boundary
     const uint32_t cend = l == S - 1 ? total_bits : (l + 1) * cw * 32;
-    const uint32_t maxfast = 32 - kp1; // a symbol with more ones than this does not fit one 32-bit window
-    uint32_t n = 0, exitp = cstart, ncp = 0;
     bool fail = false;
-    if (ok && cstart < cend) {
-        uint32_t pos = cstart, j = 0, next_cp = 0;
-        const uint32_t *wa = sw + (pos >> 5) + 1;
-        uint32_t r0 = wa[-1], r1 = wa[0];
-        while (true) {
-            if (j == next_cp) {
-                const uint32_t rel = pos - cstart;
-                if (ncp < (uint32_t)kCpMax && rel < 0xffffu)
-                    cps[ncp * 32 + lane] = (uint16_t)rel;
+    bool active = ok && cstart < cend;
+    uint32_t j = 0; // symbols parsed by completed rounds (the same for every lane still active)
+    if (active)
+        s.prime(cstart);
+    else
+        s.pos = cstart;
+    uint16_t *cpl = cps + lane;
+    while (__ballot_sync(kFull, active)) {
+        if (active) {
+            if (j)
+                s.boundary();
+            const uint32_t pos_s = s.pos;
+            const bool dense = j < 64;
+            if (!dense && ((j - 64) & 31) == 0) {
+                const uint32_t i = kCpDense + ((j - 64) >> 5), rel = pos_s - cstart;
+                if (i < (uint32_t)kCpMax && rel < 0xffffu)
+                    cpl[i * 32] = (uint16_t)rel;
                 else
                     fail = true;
-                ncp++;
-                next_cp += j < 64 ? 4 : 32;
             }
-            uint32_t pp[5];
-            pp[0] = pos;
             uint32_t mx = 0;
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const uint32_t ones = __clz(~__funnelshift_l(r1, r0, pos));
+            for (int e = 0; e < ROUND; e++) {
+                if (dense && (e & 3) == 0) { // uniform over the active lanes
+                    const uint32_t rel = s.pos - cstart;
+                    if (rel < 0xffffu)
+                        cpl[((j + e) >> 2) * 32] = (uint16_t)rel;
+                    else
+                        fail = true;
+                }
+                const uint32_t win = __funnelshift_r(s.r0, s.r1, s.pos);
+                const uint32_t ones = bfind_u32(~win & (win + 1)); // trailing ones (0xffffffff: the whole window)
                 mx = max(mx, ones);
-                const uint32_t pn = pos + ones + kp1;
-                if ((pos ^ pn) >= 32u) {
-                    r0 = r1;
-                    wa++;
-                    r1 = *wa;
+                const uint32_t pn = s.pos + ones + kp1;
+                if ((s.pos ^ pn) >= 32u)
+                    s.advance();
+                s.pos = pn;
+            }
+            if (mx > 32u - kp1) {
+                // a symbol longer than the window: redo the round with the on-demand reader, then restart the stream
+                cp_async_wait<0>();
+                rd.base_w = rd.end_w = 0;
+                uint32_t q = pos_s;
+                bool crossed = false;
+#pragma unroll 1
+                for (int e = 0; e < ROUND; e++) {
+                    q = reader_next_boundary<RING>(&rd, total_bits, q, kp1);
+                    crossed |= q >= cend;
                 }
-                pos = pn;
-                pp[e + 1] = pos;
-            }
-            if (mx > maxfast) { // a long symbol in this batch: redo it with the general step
-                uint32_t q = pp[0];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    q = rice_next_boundary(sw, total_bits, q, kp1);
-                    pp[e + 1] = q;
+                if (crossed) {
+                    s.prime(pos_s); // (the reader has overwritten the ring)
+                    active = false;
+                } else {
+                    s.prime(q);
+                    j += ROUND;
                 }
-                pos = q;
-                const uint32_t w = min(pos >> 5, total + 6);
-                wa = sw + w + 1;
-                r0 = wa[-1];
-                r1 = wa[0];
+            } else if (s.pos >= cend || j + ROUND >= (uint32_t)kFrame + 64) {
+                s.pos = pos_s; // the chunk ends inside this round: the tail loop below finds where
+                active = false;
+            } else {
+                j += ROUND;
             }
-            if (pp[4] < cend && j + 4 < (uint32_t)kFrame + 64) {
-                j += 4;
-                continue;
-            }
-            const uint32_t e = pp[1] >= cend ? 1 : pp[2] >= cend ? 2 : pp[3] >= cend ? 3 : 4;
-            n = j + e;
-            exitp = pp[e];
-            break;
         }
     }
+    // One boundary forward, keeping the streaming state valid (a top-up every ROUND symbols); a symbol longer
+    // than the window goes through the on-demand reader and restarts the stream behind it.
+    uint32_t since = 0;
+    auto step = [&]() {
+        const uint32_t win = __funnelshift_r(s.r0, s.r1, s.pos);
+        const uint32_t ones = bfind_u32(~win & (win + 1));
+        if (ones + kp1 > 32u) {
+            cp_async_wait<0>();
+            rd.base_w = rd.end_w = 0;
+            const uint32_t q = reader_next_boundary<RING>(&rd, total_bits, s.pos, kp1);
+            s.prime(q);
+            since = 0;
+        } else {
+            const uint32_t pn = s.pos + ones + kp1;
+            if ((s.pos ^ pn) >= 32u)
+                s.advance();
+            s.pos = pn;
+            if (++since == ROUND) {
+                s.boundary();
+                since = 0;
+            }
+        }
+    };
+    // ---- the tail: the round in which the chunk ends, one symbol at a time, all lanes together ----
+    uint32_t n = j, exitp = cstart;
+    bool found = !(ok && cstart < cend);
+    if (!found)
+        s.load_window(); // back at the start of that round; the ring still holds it
+    for (int e = 0; e <= ROUND && __ballot_sync(kFull, !found); e++) {
+        if (!found) {
+            if (s.pos >= cend) {
+                found = true;
+                exitp = s.pos;
+            } else {
+                if (n < 64 ? (n & 3) == 0 : ((n - 64) & 31) == 0) {
+                    const uint32_t i = cp_index(n), rel = s.pos - cstart;
+                    if (i < (uint32_t)kCpMax && rel < 0xffffu)
+                        cpl[i * 32] = (uint16_t)rel;
+                    else
+                        fail = true;
+                }
+                step();
+                n++;
+            }
+        }
+    }
+    if (!found) { // more symbols than a chunk may hold
+        fail = true;
+        exitp = s.pos;
+    }
+    const uint32_t ncp = cp_count(n);
     if (ncp > (uint32_t)kCpMax)
         fail = true;
     __syncwarp();
@@ -194,36 +432,42 @@ __global__ void __launch_bounds__(128) k_rice_split_index(RiceVsParams p)
     const uint32_t ncp_s = __shfl_down_sync(kFull, ncp, 1), n_s = __shfl_down_sync(kFull, n, 1);
     const uint32_t exit_s = __shfl_down_sync(kFull, exitp, 1), cstart_s = __shfl_down_sync(kFull, cstart, 1);
     uint32_t x = 0, m_next = 0; // overflow symbols of this lane; index (in the next lane's parse) of the merge boundary
-    if (ok && !fail && l < S - 1) {
-        uint32_t q = exitp, i = 0;
+    {
+        bool done = !(ok && !fail && l < S - 1);
+        uint32_t i = 0;
         const uint16_t *cn = cps + lane + 1;
-        for (uint32_t guard = 0;; guard++) {
-            const uint32_t rel = q - cstart_s;
-            if (rel >= 0xffffu || guard > 4096u) {
-                fail = true;
-                break;
-            }
-            while (i < ncp_s && cn[i * 32] < rel)
-                i++;
-            if (i < ncp_s) {
-                if (cn[i * 32] == rel) {
-                    m_next = cp_symbol(i);
-                    break;
-                }
-            } else if (q >= exit_s) { // behind the last checkpoint: only the next lane's exit is left to meet
-                if (q == exit_s)
-                    m_next = n_s;
-                else
+        for (uint32_t guard = 0; __ballot_sync(kFull, !done); guard++) {
+            if (!done) {
+                const uint32_t rel = s.pos - cstart_s;
+                if (rel >= 0xffffu || guard > 2048u) {
                     fail = true;
-                break;
+                    done = true;
+                } else {
+                    while (i < ncp_s && cn[i * 32] < rel)
+                        i++;
+                    if (i < ncp_s) {
+                        if (cn[i * 32] == rel) {
+                            m_next = cp_symbol(i);
+                            done = true;
+                        }
+                    } else if (s.pos >= exit_s) { // behind the last checkpoint: only the next lane's exit is left to meet
+                        if (s.pos == exit_s)
+                            m_next = n_s;
+                        else
+                            fail = true;
+                        done = true;
+                    }
+                    if (!done) {
+                        step();
+                        x++;
+                    }
+                }
             }
-            q = rice_next_boundary(sw, total_bits, q, kp1);
-            x++;
         }
     }
     // ---- phase 3: symbol index of every lane's first true boundary ----
     const uint32_t m_up = __shfl_up_sync(kFull, m_next, 1);
-    const uint32_t m = l == 0 ? 0u : m_up;         // this lane's parse is the true one from its symbol m on
+    const uint32_t m = l == 0 ? 0u : m_up; // this lane's parse is the true one from its symbol m on
     const uint32_t valid = n >= m ? n - m : 0u;
     if (n < m)
         fail = true;
@@ -252,84 +496,56 @@ __global__ void __launch_bounds__(128) k_rice_split_index(RiceVsParams p)
     const uint32_t cst_s = __shfl_sync(kFull, cstart, gb + ls), x_s = __shfl_sync(kFull, x, gb + ls);
     if (exists && l == 0)
         p.flags[st] = group_bad ? 1u : 0u;
-    if (exists && l > 0) {
-        uint32_t result = kNoSplit;
-        if (!group_bad) {
-            const uint32_t rel = target - b_s;
-            uint32_t q, walk;
-            bool found = true;
+    {
+        const bool work = exists && l > 0 && !group_bad;
+        const uint32_t rel = target - b_s;
+        uint32_t q = 0, walk = 0;
+        bool have = false;
+        if (work) {
             if (rel < valid_s) {
                 const uint32_t jj = m_s + rel, i = cp_index(jj);
                 q = cst_s + cps[i * 32 + gb + ls];
                 walk = jj - cp_symbol(i);
+                have = true;
             } else {
                 q = exitp_s;
                 walk = rel - valid_s;
-                found = walk < x_s;
+                have = walk < x_s; // else: a stream with too few symbols
             }
-            for (uint32_t t = 0; t < walk && t < 512u; t++)
-                q = rice_next_boundary(sw, total_bits, q, kp1);
-            result = found ? q - skip * 32 : 0u; // a stream with too few symbols: the decoder's end check catches it
         }
-        p.table[(size_t)st * (S - 1) + (l - 1)] = result;
+        cp_async_wait<0>();
+        if (have) {
+            s.prime(q);
+            since = 0;
+        }
+        for (uint32_t t = 0; __ballot_sync(kFull, have && t < walk); t++)
+            if (have && t < walk)
+                step();
+        if (exists && l > 0)
+            p.table[(size_t)st * (S - 1) + (l - 1)] = group_bad ? kNoSplit : have ? s.pos - skip * 32 : 0u; // 0: the decoder's end check fails
     }
 }
 
-inline size_t rice_split_smem_bytes(int log2s, uint32_t cap_words, int warps)
+template <int RING>
+constexpr size_t split_smem_bytes()
 {
-    const int W = 32 >> log2s;
-    return (size_t)warps * W * (cap_words + 8) * 4 + (size_t)warps * kCpMax * 32 * 2;
+    return RING * 4 + (size_t)kVsWarps * 32 * RING * 4 + (size_t)kVsWarps * kCpMax * 32 * 2;
 }
 
 // --------------------------------------------------------------- virtual streams --
+//
+// Geometry (template parameters; the launch picks one):
+//   RING   words per lane in the shared-memory ring
+//   ROUND  symbols a lane decodes between two ring top-ups
+//   TILE   symbols per lane staged in shared memory before they leave as 4*TILE-byte row segments
 
-constexpr int kVsRing = 64;        // ring words per lane: one 256-byte row
-constexpr int kVsRound = 16;       // symbols per lane between two ring top-ups
-constexpr int kVsTilePitch = 36;   // words; 32 symbols per lane per flush, rows 16-byte aligned and bank-rotated
-constexpr int kVsWarps = 4;
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-
-// A lane's ring: 64 words in one 256-byte row of shared memory, word w at byte ((4w + rot) & 255)
-// of the row (rot = 16 * lane spreads the lanes over the banks).
-struct VsRing {
-    uint32_t row, rot;  // shared-space byte address of the row (256-aligned); rotation
-    const uint4 *gvec;  // the stream from its 16-byte aligned base
-    int total_bytes;    // bytes from gvec to the end of the stream; everything behind reads as zero
-    __device__ __forceinline__ uint32_t word_addr(uint32_t w) const { return row | ((4 * w + rot) & (kVsRing * 4 - 1)); }
-    __device__ __forceinline__ uint32_t word(uint32_t w) const { return lds_u32(word_addr(w)); } // reversed words only (below `ce`)
-    __device__ __forceinline__ void issue(uint32_t fv) const // vector fv: words [4fv, 4fv+4)
-    {
-        const int rem = total_bytes - (int)(16 * fv);
-        const uint32_t sz = rem <= 0 ? 0u : rem < 16 ? (uint32_t)rem : 16u;
-        const uint4 *src = gvec + (sz ? fv : 0u);
-        const uint32_t dst = row | ((16 * fv + rot) & (kVsRing * 4 - 1));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-    }
-    // The parser wants the stream MSB first (leading-zero count finds the terminator, the payload reads as a
-    // number); BREV costs three issue slots on sm_100a, so the words are reversed once, in place, when their
-    // vector has landed -- not once per symbol.
-    __device__ __forceinline__ void reverse(uint32_t v) const
-    {
-        const uint32_t a = row | ((16 * v + rot) & (kVsRing * 4 - 1));
-        uint32_t x, y, z, w;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
-        x = __brev(x), y = __brev(y), z = __brev(z), w = __brev(w);
-        asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x), "r"(y), "r"(z), "r"(w), "r"(a) : "memory");
-    }
-};
-
-// General decode of `count` symbols from bit `pos`, ring words only up to `ce` (exclusive, complete).
+// General decode of `count` symbols from bit `pos`, ring words (reversed) only up to `ce` (exclusive).
 // Out of line: runs for the rare round that holds a symbol longer than one 32-bit window.
 // Returns false if it would need words the ring does not hold (the stream is then flagged).
-__device__ __noinline__ bool vs_slow_round(const VsRing rg, uint32_t ce, uint32_t &pos, uint32_t k, int32_t *dst, int count)
+template <int RING>
+__device__ __noinline__ bool vs_slow_round(const VsRing<RING> rg, uint32_t ce, uint32_t *pos, uint32_t k, int32_t *dst, int count)
 {
-    uint32_t q = pos;
+    uint32_t q = *pos;
     for (int e = 0; e < count; e++) {
         uint32_t ones = 0;
         while (true) {
@@ -351,21 +567,24 @@ __device__ __noinline__ bool vs_slow_round(const VsRing rg, uint32_t ce, uint32_
         q += k;
         dst[e] = unzigzag((ones << k) | pay); // uint32 shift as in rice_decoder.cpp:37
     }
-    if ((q >> 5) + 2 > ce)
+    if ((q >> 5) + 3 > ce)
         return false;
-    pos = q;
+    *pos = q;
     return true;
 }
 
+template <int RING, int ROUND, int TILE>
 __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p, int log2s)
 {
+    static_assert(TILE % ROUND == 0 && TILE % 4 == 0 && ROUND % 4 == 0 && TILE <= 32, "tile geometry");
+    constexpr int kTilePitch = TILE + 4;       // words: rows stay 16-byte aligned, banks rotate by 4 per row
+    constexpr int kRowLanes = TILE / 4;        // lanes that move one row segment (16 bytes each)
+    constexpr int kRowsPerIt = 32 / kRowLanes; // rows per store instruction
     extern __shared__ __align__(16) unsigned char vs_smem[];
     const int lane = lane_id(), warp = warp_id();
-    // ring rows must be 256-byte aligned in the shared window (the word address is formed with an OR)
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(vs_smem);
-    const uint32_t pad = (256u - (smem0 & 255u)) & 255u;
-    const uint32_t ring_base = smem0 + pad + (uint32_t)(warp * 32 + lane) * (kVsRing * 4);
-    int32_t *tile = reinterpret_cast<int32_t *>(vs_smem + pad + kVsWarps * 32 * kVsRing * 4) + warp * 32 * kVsTilePitch;
+    const uint32_t pad = (RING * 4 - (smem0 & (RING * 4 - 1))) & (RING * 4 - 1);
+    int32_t *tile = reinterpret_cast<int32_t *>(vs_smem + pad + kVsWarps * 32 * RING * 4) + warp * 32 * kTilePitch;
 
     const uint32_t S = 1u << log2s, part = (uint32_t)kFrame >> log2s;
     const uint32_t v0 = (blockIdx.x * kVsWarps + warp) * 32;
@@ -394,127 +613,91 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p.words + (ok ? d.res_offset : 0));
     const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
     const uint32_t total = ok && d.res_words ? (uint32_t)d.res_words + skip : 0u;
-    VsRing rg;
-    rg.row = ring_base;
-    rg.rot = (16u * lane) & (kVsRing * 4 - 1);
-    rg.gvec = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
-    rg.total_bytes = (int)(total * 4);
+    using Stream = VsStream<RING, ROUND, true>;
+    Stream s;
+    s.rg.row = smem0 + pad + (uint32_t)(warp * 32 + lane) * (RING * 4);
+    s.rg.rot = (16u * lane) & (RING * 4 - 1);
+    s.rg.gvec = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    s.rg.total_bytes = (int)(total * 4);
     const uint32_t k = ok ? d.res_rice_param : 0u, kp1 = k + 1, kk = 32 - k, kpow = 1u << k;
-    const uint32_t maxfast = 32 - kp1;
     const uint32_t row_mask = __ballot_sync(kFull, store_row);
 
-    // ---- prime the ring ----
-    uint32_t pos = sb + 32 * skip;
-    if (pos > total * 32 + 64)
-        pos = total * 32 + 64; // a nonsense table entry: parse zeros, fail the end check
-    uint32_t wb = (pos >> 5) + 1; // r1 holds word wb, r0 word wb - 1
-    uint32_t fv = (wb - 1) >> 2;
-    // vector fv overwrites words [4fv - 64, 4fv - 61]; everything below wb - 1 is dead
-    {
-        const uint32_t lim = (wb + kVsRing - 5) >> 2;
-        while (fv <= lim) {
-            rg.issue(fv);
-            fv++;
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint32_t rv = (wb - 1) >> 2; // vectors below rv are reversed
-    while (rv < fv) {
-        rg.reverse(rv);
-        rv++;
-    }
-    uint32_t ce = 4 * fv, cv_next = fv; // words below ce are in the ring, reversed; vectors below cv_next have been requested
-    uint32_t r0 = rg.word(wb - 1), r1 = rg.word(wb);
-    uint32_t wa = 4 * wb + rg.rot;      // running byte offset of word wb
+    uint32_t p0 = sb + 32 * skip;
+    if (p0 > total * 32 + 64)
+        p0 = total * 32 + 64; // a nonsense table entry: parse zeros, fail the end check
+    s.prime(p0);
     bool dead = false;
 
     int32_t *out_warp = p.out + (size_t)v0 * part;
-    const uint32_t n_rounds = part / kVsRound;
+    const uint32_t n_rounds = part / ROUND;
+    const uint32_t c_pn = kp1 + 31;
 #pragma unroll 1
     for (uint32_t r = 0; r < n_rounds; r++) {
-        // ---- boundary: top the ring up, retire the previous top-up ----
-        if (r) {
-            const uint32_t lim = (wb + kVsRing - 5) >> 2;
-            while (fv <= lim) {
-                rg.issue(fv);
-                fv++;
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
-            while (rv < cv_next) {
-                rg.reverse(rv);
-                rv++;
-            }
-            ce = 4 * cv_next;
-            cv_next = fv;
-        }
-        const uint32_t pos_s = pos;
-        uint32_t mx = 0;
-        int32_t *trow = tile + lane * kVsTilePitch + (r & 1) * kVsRound;
+        if (r && !dead)
+            s.boundary();
+        uint32_t pos_s = s.pos;
+        int mn = 31; // lowest FLO result of the round; below k: a symbol longer than the window
+        int32_t *trow = tile + lane * kTilePitch + (r % (TILE / ROUND)) * ROUND;
 #pragma unroll
-        for (int e4 = 0; e4 < kVsRound; e4 += 4) {
+        for (int e4 = 0; e4 < ROUND; e4 += 4) {
             int32_t val[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const uint32_t win = __funnelshift_l(r1, r0, pos);
-                const uint32_t ones = __clz(~win);
-                mx = max(mx, ones);
+                const uint32_t win = __funnelshift_l(s.r1, s.r0, s.pos);
+                const uint32_t f = bfind_u32(~win);   // 31 - ones; 0xffffffff: the window is all ones
+                const uint32_t pn = s.pos + c_pn - f; // pos + ones + 1 + k
+                mn = min(mn, (int)f);
+                const uint32_t ones = 31 - f;
                 const uint32_t t = __funnelshift_lc(0u, win, ones + 1);
                 const uint32_t pay = __funnelshift_rc(t, 0u, kk);
-                const uint32_t u = ones * kpow + pay;
-                val[e] = unzigzag(u);
-                const uint32_t pn = pos + ones + kp1;
-                if ((pos ^ pn) >= 32u) {
-                    r0 = r1;
-                    wa += 4;
-                    r1 = lds_u32(rg.row | (wa & (kVsRing * 4 - 1)));
-                }
-                pos = pn;
+                val[e] = unzigzag3(ones * kpow + pay);
+                if ((s.pos ^ pn) >= 32u)
+                    s.advance();
+                s.pos = pn;
             }
             *reinterpret_cast<int4 *>(trow + e4) = make_int4(val[0], val[1], val[2], val[3]);
         }
-        if (mx > maxfast && !dead) { // a symbol longer than the window: redo the round with the general parser
-            pos = pos_s;
-            if (vs_slow_round(rg, ce, pos, k, trow, kVsRound)) {
-                wb = (pos >> 5) + 1;
-                r0 = rg.word(wb - 1);
-                r1 = rg.word(wb);
-                wa = 4 * wb + rg.rot;
+        if (mn < (int)k && !dead) { // a symbol longer than the window: redo the round with the general parser
+            if (vs_slow_round<RING>(s.rg, s.ce, &pos_s, k, trow, ROUND)) {
+                s.pos = pos_s;
+                s.load_window();
             } else {
                 dead = true;
             }
         }
-        wb = dead ? wb : (pos >> 5) + 1;
-        // ---- every second round: 32 symbols per lane leave as whole 128-byte lines ----
-        if (r & 1) {
+        // ---- a full tile: TILE symbols per lane leave as row segments of 4*TILE bytes ----
+        if (r % (TILE / ROUND) == TILE / ROUND - 1) {
             __syncwarp();
-            int32_t *dst = out_warp + (size_t)(r >> 1) * 32 + (lane & 7) * 4;
+            int32_t *dst = out_warp + (size_t)(r / (TILE / ROUND)) * TILE + (lane % kRowLanes) * 4;
 #pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int row = 4 * it + (lane >> 3);
+            for (int it = 0; it < 32 / kRowsPerIt; it++) {
+                const int row = kRowsPerIt * it + lane / kRowLanes;
                 if ((row_mask >> row) & 1u) {
-                    const int4 q = *reinterpret_cast<const int4 *>(tile + row * kVsTilePitch + (lane & 7) * 4);
+                    const int4 q = *reinterpret_cast<const int4 *>(tile + row * kTilePitch + (lane % kRowLanes) * 4);
                     *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
                 }
             }
             __syncwarp();
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cp_async_wait<0>();
     if (exists && store_row) {
         bool bad = dead;
         if (ok) {
             if (expect_end != kNoSplit)
-                bad |= pos - 32 * skip != expect_end;
+                bad |= s.pos - 32 * skip != expect_end;
             else
-                bad |= pos > total * 32;
+                bad |= s.pos > total * 32;
         }
         if (bad)
             p.flags[st] = 1u; // (several parts may say so: idempotent)
     }
 }
 
-constexpr size_t kVsSmemBytes = 256 + (size_t)kVsWarps * 32 * kVsRing * 4 + (size_t)kVsWarps * 32 * kVsTilePitch * 4;
+template <int RING, int TILE>
+constexpr size_t vs_smem_bytes()
+{
+    return RING * 4 + (size_t)kVsWarps * 32 * RING * 4 + (size_t)kVsWarps * 32 * (TILE + 4) * 4;
+}
 
 } // namespace selab200

@@ -303,3 +303,176 @@ def decode_file_sharded(sela_path, wav_path, frame_offsets_fn, decode_fn):
         _pwrite_all(wav_path, pcm.view(np.uint8).reshape(-1), 44 + lo * stride)
     dist.barrier()
     return n_frames
+
+
+# ------------------------------------------------------- device-resident sharding --
+#
+# The same scatter / code / gather with every buffer in HBM (NCCL moves device memory; the only
+# host<->device traffic left is the root's own upload of the file and download of the result).
+# `DeviceCodec` (sela_b200/device.py) does the local coding through the *_device C-ABI calls.
+
+def _timed(fn, dev):
+    """Run fn() between two CUDA events on the current stream; returns (result, milliseconds)."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return out, a.elapsed_time(b)
+
+
+def scatter_frames_device(pcm_dev, n_frames, channels, src=0):
+    """pcm_dev: on `src` an int16 CUDA tensor with the whole interleaved file; returns this rank's block (a
+    CUDA int16 tensor; on `src` a view of pcm_dev)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = frame_block(n_frames, rank, world)
+    per = FRAME * channels
+    if rank == src:
+        ops = []
+        for r in range(world):
+            a, b = frame_block(n_frames, r, world)
+            if r != src and b > a:
+                ops.append(dist.P2POp(dist.isend, pcm_dev[a * per:b * per], r))
+        _p2p(ops)
+        return pcm_dev[lo * per:hi * per]
+    buf = torch.empty((hi - lo) * per, dtype=torch.int16, device=_dev())
+    if hi > lo:
+        _p2p([dist.P2POp(dist.irecv, buf, src)])
+    return buf
+
+
+def gather_encoded_device(descs_dev, words_dev, n_words, n_frames, channels, dst=0):
+    """descs_dev: uint8 CUDA tensor (32 bytes per subframe of this rank's block), words_dev: int32 CUDA tensor,
+    n_words: words used.  On `dst` returns (descs, words) for the whole file, offsets re-based, both on the
+    device; elsewhere (None, None)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = torch.tensor([n_words], dtype=torch.int64, device=_dev())
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine)
+    sizes = [int(t.item()) for t in sizes]
+    if rank != dst:
+        ops = []
+        if descs_dev.numel():
+            ops.append(dist.P2POp(dist.isend, descs_dev, dst))
+        if n_words:
+            ops.append(dist.P2POp(dist.isend, words_dev[:n_words], dst))
+        _p2p(ops)
+        return None, None
+    all_descs = torch.empty(n_frames * channels * 32, dtype=torch.uint8, device=_dev())
+    all_words = torch.empty(sum(sizes) + 8, dtype=torch.int32, device=_dev())
+    ops, base = [], 0
+    bases = []
+    for r in range(world):
+        a, b = frame_block(n_frames, r, world)
+        bases.append(base)
+        d_view = all_descs[a * channels * 32:b * channels * 32]
+        w_view = all_words[base:base + sizes[r]]
+        if r == dst:
+            d_view.copy_(descs_dev)
+            w_view.copy_(words_dev[:sizes[r]])
+        else:
+            if b > a:
+                ops.append(dist.P2POp(dist.irecv, d_view, r))
+            if sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, w_view, r))
+        base += sizes[r]
+    _p2p(ops)
+    # re-base the two word offsets of every descriptor (int64 fields at bytes 16 and 24 of the 32-byte record)
+    table = all_descs.view(torch.int64).view(-1, 4)
+    for r in range(world):
+        a, b = frame_block(n_frames, r, world)
+        if b > a and bases[r]:
+            table[a * channels:b * channels, 2:4] += bases[r]
+    return all_descs, all_words[:base]
+
+
+def encode_sharded_device(pcm_dev, n_frames, channels, root=0):
+    """Scatter (NCCL) -> device-resident encode on every rank -> gather (NCCL).  Returns
+    ((descs, words) on root / (None, None) elsewhere, {'scatter_ms', 'encode_ms', 'gather_ms'})."""
+    from .device import DeviceCodec
+    dev = _dev()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = frame_block(n_frames, rank, world)
+    block, t_scatter = _timed(lambda: scatter_frames_device(pcm_dev, n_frames, channels, src=root), dev)
+    codec = DeviceCodec(max(hi - lo, 1), channels, device=dev.index)
+
+    def run():
+        if hi > lo:
+            codec.encode(block.contiguous())
+    _, t_enc = _timed(run, dev)
+    codec.check_status()
+    n_words = int(codec.words_used.item()) if hi > lo else 0
+    descs = codec.descs if hi > lo else codec.descs[:0]
+    out, t_gather = _timed(lambda: gather_encoded_device(descs, codec.words, n_words, n_frames, channels, dst=root), dev)
+    return out, {"scatter_ms": t_scatter, "encode_ms": t_enc, "gather_ms": t_gather}
+
+
+def decode_sharded_device(descs_dev, words_dev, n_frames, channels, root=0):
+    """Root holds (descs, words) on the device; each rank decodes its block of frames on its GPU; the PCM is
+    gathered on root (int16 CUDA tensor; None elsewhere).  Returns (pcm, timings)."""
+    from .device import DeviceCodec
+    dev = _dev()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = frame_block(n_frames, rank, world)
+    per = FRAME * channels
+
+    def scatter():
+        if rank == root:
+            table = descs_dev.view(torch.int64).view(-1, 4)
+            ops, mine = [], None
+            for r in range(world):
+                a, b = frame_block(n_frames, r, world)
+                if b <= a:
+                    continue
+                d = descs_dev[a * channels * 32:b * channels * 32].clone()
+                t = d.view(torch.int64).view(-1, 4)
+                w_lo = int(torch.minimum(t[:, 2], t[:, 3]).min().item())
+                rec = descs_dev[(b * channels - 1) * 32:(b * channels) * 32].cpu().numpy().view(DESC_DTYPE)[0]
+                w_hi = max(int(rec["refl_offset"]) + int(rec["refl_words"]), int(rec["res_offset"]) + int(rec["res_words"]))
+                t[:, 2:4] -= w_lo
+                w = words_dev[w_lo:w_hi]
+                if r == root:
+                    mine = (d, w.clone())
+                    continue
+                hdr = torch.tensor([w_hi - w_lo], dtype=torch.int64, device=dev)
+                ops += [dist.P2POp(dist.isend, hdr, r), dist.P2POp(dist.isend, d, r), dist.P2POp(dist.isend, w, r)]
+            _p2p(ops)
+            return mine if mine is not None else (descs_dev[:0], words_dev[:0])
+        if hi <= lo:
+            return torch.empty(0, dtype=torch.uint8, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
+        hdr = torch.zeros(1, dtype=torch.int64, device=dev)
+        d = torch.empty((hi - lo) * channels * 32, dtype=torch.uint8, device=dev)
+        _p2p([dist.P2POp(dist.irecv, hdr, root), dist.P2POp(dist.irecv, d, root)])
+        w = torch.empty(int(hdr.item()) + 8, dtype=torch.int32, device=dev)
+        _p2p([dist.P2POp(dist.irecv, w[:int(hdr.item())], root)])
+        return d, w[:int(hdr.item())]
+
+    (d, w), t_scatter = _timed(scatter, dev)
+    codec = DeviceCodec(max(hi - lo, 1), channels, device=dev.index, words_capacity=max(int(w.numel()), 1) + 8)
+    local = torch.empty((hi - lo) * per, dtype=torch.int16, device=dev)
+
+    def run():
+        if hi > lo:
+            codec.descs.copy_(d)
+            codec.words[:w.numel()].copy_(w)
+            codec.decode(local, int(w.numel()))
+    _, t_dec = _timed(run, dev)
+    codec.check_status()
+
+    def gather():
+        if rank != root:
+            if hi > lo:
+                _p2p([dist.P2POp(dist.isend, local, root)])
+            return None
+        out = torch.empty(n_frames * per, dtype=torch.int16, device=dev)
+        ops = []
+        for r in range(world):
+            a, b = frame_block(n_frames, r, world)
+            if r == root:
+                out[a * per:b * per].copy_(local)
+            elif b > a:
+                ops.append(dist.P2POp(dist.irecv, out[a * per:b * per], r))
+        _p2p(ops)
+        return out
+    out, t_gather = _timed(gather, dev)
+    return out, {"scatter_ms": t_scatter, "decode_ms": t_dec, "gather_ms": t_gather}

@@ -20,11 +20,14 @@ ap.add_argument("--tiles", default="1,4,16,48,96")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--warm", type=int, default=3)
 ap.add_argument("--out", default="gpurun_out/rice_decode_roofline.json")
+ap.add_argument("--frames", type=int, default=0, help="use only the first N frames of the file (small-batch sweep)")
 ap.add_argument("--splits", default="auto", help="comma list of SELAB200_RICE_SPLIT values (auto = library default)")
 args = ap.parse_args()
 max_tile = args.max_tile
 TILES = [int(t) for t in args.tiles.split(",")]
 pcm = synth.sine_noise(44100, 2, seconds=600, seed=1)
+if args.frames:
+    pcm = pcm[: args.frames * 2048]
 n_frames = pcm.shape[0] // 2048
 codec = DeviceCodec(n_frames, 2)
 codec.encode(torch.from_numpy(pcm.reshape(-1)).cuda()); torch.cuda.synchronize(); codec.check_status()

@@ -227,10 +227,13 @@ def sharded_block(args, rank, world, dev, dist):
     if rank == 0:
         base = torch.from_numpy(synth.sine_noise(rate, ch, n_frames=n_base, seed=2).reshape(-1))
         pcm_dev = torch.empty(n_frames * per, dtype=torch.int16, device=dev)
+        base_pinned = base.pin_memory()
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        base_dev = base.pin_memory().to(dev, non_blocking=True)
+        base_dev = base_pinned.to(dev, non_blocking=True)
         torch.cuda.synchronize(dev)
         h2d_s = time.perf_counter() - t0
+        del base_pinned
         for r in range(reps):
             pcm_dev[r * n_base * per:(r + 1) * n_base * per].copy_(base_dev)
         del base_dev
@@ -568,17 +571,7 @@ def run_ours(args, rank, world, local_rank):
             pcie = pcie_probe(dev)
         except Exception as e:
             pcie = {"error": repr(e)[:300]}
-    sharded = None
-    if not args.no_sharded:
-        del pcm, out
-        torch.cuda.empty_cache()
-        try:
-            sharded = sharded_block(args, rank, world, dev, dist)
-        except Exception as e:
-            sharded = {"error": repr(e)[:400]}
-            if dist:
-                raise                                # a rank that drops out of a collective must not hang the others silently
-
+    line = None
     if rank == 0:
         desc_bytes = n_frames * CHANNELS * 32
         prof, stale = measured_profile("k_encode_units<stereo>")
@@ -618,7 +611,6 @@ def run_ours(args, rank, world, local_rank):
                                  "read+write per launch from profiles/traffic.json (ncu), traffic_stale = kernel sources "
                                  "changed since that capture"},
             "roofline_rice_decode": rice,
-            "sharded": sharded,
         }
         if world == 1 and not args.no_cpu:
             info, (sf, d_ref, w_ref) = cpu_reference_leg(pcm_np)
@@ -627,6 +619,38 @@ def run_ours(args, rank, world, local_rank):
             descs_gpu = codec.descs.cpu().numpy().view(_lib.DESC_DTYPE)[: sf * CHANNELS]
             words_gpu = codec.words[: int(descs_gpu[-1]["res_offset"]) + int(descs_gpu[-1]["res_words"])].cpu().numpy().view(np.uint32)
             line["bit_exact_vs_cpu"] = bool(descs_gpu.tobytes() == d_ref.tobytes() and np.array_equal(words_gpu, w_ref))
+
+    # ---------------- configs[3] / [4]: one file across the ranks, a batch of files per rank ----------------
+    # The headline above is complete at this point.  The sharded block runs collectives of its own; should a
+    # rank fail or stall in it, a watchdog lets rank 0 print the line without it instead of losing the run.
+    if not args.no_sharded:
+        import threading
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(args.sharded_timeout):
+                if rank == 0:
+                    line["sharded"] = {"error": "sharded block did not finish within %d s" % args.sharded_timeout}
+                    emit_line(line)
+                os._exit(0)
+        if dist:
+            threading.Thread(target=watchdog, daemon=True).start()
+        del pcm, out
+        torch.cuda.empty_cache()
+        try:
+            sharded = sharded_block(args, rank, world, dev, dist)
+        except Exception as e:
+            sharded = {"error": repr(e)[:400]}
+            if dist:                                 # the other ranks may be waiting for this one: do not join them again
+                if rank == 0:
+                    line["sharded"] = sharded
+                    emit_line(line)
+                done.set()
+                os._exit(0)
+        done.set()
+        if rank == 0:
+            line["sharded"] = sharded
+    if rank == 0:
         emit_line(line)
     for p in (p1, p2, p3, p4):
         L.selab200_host_free(p)
@@ -643,6 +667,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the configs[3]/[4] block (profiling runs)")
     ap.add_argument("--sharded-minutes", type=int, default=0, help="length of the config-4 file (default 60)")
+    ap.add_argument("--sharded-timeout", type=int, default=240, help="seconds before the sharded block is given up (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -17,9 +17,10 @@
  *     error convention (src/include/data/exception.hpp:7-14, src/main.cpp:101-105).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point
  *     fails with SELAB200_ERR_NO_DEVICE.
- *   - one process drives one GPU (selab200_init(device)); calls are synchronous
- *     unless they take a stream (the *_device forms), and are serialised by an
- *     internal mutex.
+ *   - one process drives one GPU (selab200_init(device)) or several
+ *     (selab200_init_devices); calls are synchronous unless they take a stream
+ *     (the *_device forms), and are serialised by an internal mutex -- inside a
+ *     call every device works on its own thread with its own context.
  *   - a "subframe" is one channel of one 2048-sample frame
  *     (src/include/file/wav_file.hpp:12); frames are independent.
  */
@@ -70,9 +71,20 @@ typedef struct selab200_subframe_desc {
 
 /* ------------------------------------------------------------ life cycle -- */
 
-/* Bind this process to CUDA device `device` (>= 0) and create the stream and
- * workspace.  Idempotent for the same device. */
+/* Bind this process to CUDA device `device` (>= 0) and create the streams and
+ * workspace.  Idempotent for the same device; a different device than before
+ * tears the old context down first (its streams and pools belong to the old device). */
 int  selab200_init(int device);
+/* Several devices of one box (selagpu_init(device_count, device_ids)): every device gets a
+ * context of its own (streams, events, pools).  The host-buffer batch calls (selab200_encode_frames,
+ * selab200_decode_frames, selab200_encode_container) then cut the frames into one contiguous block per device
+ * -- n/D frames each, the last device takes the rest, the way sela::Encoder::processFrames cuts them for its
+ * threads (src/sela/encoder.cpp:58-73) -- and run the blocks concurrently, reading and writing disjoint ranges
+ * of the caller's buffers; results are byte-identical to a single device's.  devices[0] is the primary: it
+ * serves the stage-level and container-decode calls.  The *_device forms run on whichever initialised device
+ * owns the buffers they are given. */
+int  selab200_init_devices(int count, const int *devices);
+int  selab200_device_count(void);
 void selab200_shutdown(void);
 const char *selab200_last_error(void);
 int  selab200_abi_version(void);

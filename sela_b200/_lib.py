@@ -47,6 +47,8 @@ _lib = None
 _V, _U32, _SZ, _I = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _SIGNATURES = {
     "selab200_init": (_I, [_I]),
+    "selab200_init_devices": (_I, [_I, _V]),
+    "selab200_device_count": (_I, []),
     "selab200_shutdown": (None, []),
     "selab200_last_error": (C.c_char_p, []),
     "selab200_abi_version": (_I, []),
@@ -105,7 +107,10 @@ _initialised = None
 
 
 def init(device=0):
+    """Bind the library to `device` (an int) or to several devices (a list/tuple: device[0] is the primary)."""
     global _initialised
-    if _initialised != device:
-        check(lib().selab200_init(device))
-        _initialised = device
+    key = tuple(device) if isinstance(device, (list, tuple)) else (device,)
+    if _initialised != key:
+        arr = (C.c_int * len(key))(*key)
+        check(lib().selab200_init_devices(len(key), C.addressof(arr)))
+        _initialised = key

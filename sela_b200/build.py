@@ -36,12 +36,15 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    tmp = LIB.with_suffix(".so.tmp")           # built aside and renamed: a reader (or a snapshot) never sees half a library
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(tmp), *map(str, SOURCES)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("nvcc failed building %s" % LIB)
+    tmp.replace(LIB)
     (PKG / "build_ptxas.log").write_text(proc.stdout + proc.stderr)
     return LIB
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -81,7 +82,19 @@ struct Context {
     unsigned long long *h_totals = nullptr;        // pinned: arena fill level after each chunk
     size_t last_rice_n_sub = 0;                    // selab200_rice_decode_frames_device bookkeeping (flag count query)
     cudaStream_t last_rice_stream = nullptr;
-} g;
+    std::vector<struct ContainerBuffers> *spare = nullptr; // recycled container buffers of this device
+};
+
+// One context per device the library was initialised for (selab200_init / selab200_init_devices), slot 0 the
+// primary.  Everything below reaches "the" context through `g`, a thread-local pointer: an API call runs on
+// the primary (or, for the *_device forms, on the device that owns the caller's pointers); the multi-device
+// host-buffer calls give every device a worker thread of its own that points `g` at that device's context.
+// Contexts share nothing, so the workers never contend.
+constexpr int kMaxDevices = 16;
+Context g_slots[kMaxDevices];
+int g_n_ctx = 0;
+thread_local Context *tl_ctx = &g_slots[0];
+#define g (*tl_ctx)
 
 // What a container handle owns besides the walk result: the device image of the bytes, a pinned
 // descriptor table and the upload events.  Recycled through a small free list, because a process
@@ -111,7 +124,8 @@ struct ContainerBuffers {
     }
 };
 
-std::vector<ContainerBuffers> g_spare_buffers; // guarded by g_mutex
+std::vector<ContainerBuffers> g_spare_store[kMaxDevices]; // guarded by g_mutex; Context::spare points here
+#define g_spare_buffers (*g.spare)
 constexpr size_t kMaxSpareBuffers = 16;
 
 // On every exit from a pipelined call -- error paths included -- nothing may still be
@@ -201,15 +215,39 @@ const char *status_text(int s)
     }
 }
 
+// Points `g` at the primary context for the calling thread (g_mutex held) and selects its device.
 int require_ready()
 {
-    if (!g.ready)
+    tl_ctx = &g_slots[0];
+    if (g_n_ctx == 0 || !g.ready)
         return fail(SELAB200_ERR_NOT_INIT, "selab200_init() has not been called (or found no CUDA device)");
     // the current device is per host thread; callers may arrive on a thread other than init()'s
     cudaError_t e = cudaSetDevice(g.device);
     if (e != cudaSuccess)
         return fail(SELAB200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g.device, cudaGetErrorString(e));
     return 0;
+}
+
+// The *_device forms run on the device that owns the caller's buffers: points `g` at that device's context.
+int require_ready_for(const void *device_ptr)
+{
+    if (g_n_ctx == 0)
+        return require_ready();
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(SELAB200_ERR_ARGUMENT, "not a device pointer");
+    }
+    for (int i = 0; i < g_n_ctx; i++)
+        if (g_slots[i].ready && g_slots[i].device == attr.device) {
+            tl_ctx = &g_slots[i];
+            cudaError_t e = cudaSetDevice(g.device);
+            if (e != cudaSuccess)
+                return fail(SELAB200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g.device, cudaGetErrorString(e));
+            return 0;
+        }
+    return fail(SELAB200_ERR_ARGUMENT, "the buffers live on device %d, which the library was not initialised for "
+                                       "(selab200_init / selab200_init_devices)", attr.device);
 }
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -262,6 +300,8 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     if (ws_bytes < selab200_encode_workspace_bytes(n_frames, channels))
         return fail(SELAB200_ERR_ARGUMENT, "encode workspace too small");
+    if (channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) // the stereo kernel reads 16 bytes (4 sample pairs) at a time
+        return fail(SELAB200_ERR_ARGUMENT, "stereo PCM must be 16-byte aligned on the device");
     if (fresh) {
         CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
         CUDA_TRY(cudaMemsetAsync(d_used, 0, sizeof(uint64_t), stream));
@@ -342,9 +382,11 @@ int rice_split_log2(size_t n_sub)
     // Measured on B200 (profiles/r02_rice_decode_roofline.json): from about 20 000 streams up one lane per stream
     // (S = 1) through k_rice_decode_vs is fastest -- the two split passes cost more than the extra warps bring
     // once every SM has a few warps of its own; below that the machine is starved and cutting the streams
-    // wins.
+    // wins (500 streams: S = 16 is 3.5x the first-generation kernel, 8 000 streams: S = 8 is 1.9x).
+    if (n_sub >= 20000)
+        return 0;
     int l = 0;
-    while (l < 4 && (n_sub << l) < (size_t)20000)
+    while (l < 4 && (n_sub << l) < (size_t)40000)
         l++;
     return l;
 }
@@ -492,60 +534,48 @@ int selab200_abi_version(void) { return SELAB200_ABI_VERSION; }
 const char *selab200_last_error(void) { return g_error; }
 uint64_t selab200_launch_count(void) { return g_launches.load(); }
 
-int selab200_init(int device)
+// (g_mutex held; `g` points at the slot to set up)
+static int init_slot(int device, int slot)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (g.ready && g.device == device)
-        return 0;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(SELAB200_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
-                    e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
-    if (device < 0 || device >= count)
-        return fail(SELAB200_ERR_ARGUMENT, "device %d out of range (have %d)", device, count);
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return fail(SELAB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
                     prop.major, prop.minor);
-    if (!g.stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < kLanes; i++)
-            CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < kLanes; i++)
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.s_compute[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_scan[i], cudaEventDisableTiming));
     }
-    if (!g.events) {
-        for (int i = 0; i < kMaxChunks; i++) {
-            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&g.ev_scan[i], cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
-        g.events = true;
-    }
-    if (!g.h_small)
-        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_small), 64));
-    if (!g.h_totals)
-        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_totals), (kMaxChunks + 1) * 8));
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
+    g.events = true;
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_small), 64));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_totals), (kMaxChunks + 1) * 8));
     if (int rc = g.small.ensure(256))
         return rc;
+    g.spare = &g_spare_store[slot];
     g.device = device;
     g.ready = true;
     return 0;
 }
 
-void selab200_shutdown(void)
+static void shutdown_slot()
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (!g.ready)
-        return;
-    cudaStreamSynchronize(g.stream);
-    for (ContainerBuffers &b : g_spare_buffers)
-        b.destroy();
-    g_spare_buffers.clear();
+    if (g.device >= 0)
+        cudaSetDevice(g.device);
+    if (g.stream)
+        cudaStreamSynchronize(g.stream);
+    if (g.spare) {
+        for (ContainerBuffers &b : *g.spare)
+            b.destroy();
+        g.spare->clear();
+    }
     g.in.release();
     g.descs.release();
     g.words.release();
@@ -569,16 +599,86 @@ void selab200_shutdown(void)
         g.s_compute[i] = nullptr;
     }
     g.stream = g.s_h2d = g.s_d2h = nullptr;
-    if (g.events)
+    if (g.events) {
         for (int i = 0; i < kMaxChunks; i++) {
             cudaEventDestroy(g.ev_h2d[i]);
             cudaEventDestroy(g.ev_done[i]);
             cudaEventDestroy(g.ev_scan[i]);
         }
-    if (g.events)
         cudaEventDestroy(g.ev_reset);
+    }
     g.events = false;
     g.ready = false;
+    g.device = -1;
+    g.last_rice_n_sub = 0;
+}
+
+static void shutdown_all()
+{
+    for (int i = 0; i < g_n_ctx; i++) {
+        tl_ctx = &g_slots[i];
+        shutdown_slot();
+    }
+    g_n_ctx = 0;
+    tl_ctx = &g_slots[0];
+}
+
+int selab200_init_devices(int count, const int *devices)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (count < 1 || count > kMaxDevices || !devices)
+        return fail(SELAB200_ERR_ARGUMENT, "device count must be in [1, %d]", kMaxDevices);
+    bool same = count == g_n_ctx;
+    for (int i = 0; same && i < count; i++)
+        same = g_slots[i].ready && g_slots[i].device == devices[i];
+    if (same) {
+        tl_ctx = &g_slots[0];
+        return 0;
+    }
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have == 0)
+        return fail(SELAB200_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
+    for (int i = 0; i < count; i++) {
+        if (devices[i] < 0 || devices[i] >= have)
+            return fail(SELAB200_ERR_ARGUMENT, "device %d out of range (have %d)", devices[i], have);
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i])
+                return fail(SELAB200_ERR_ARGUMENT, "device %d listed twice", devices[i]);
+    }
+    // a different set of devices than before: everything the old contexts own (streams, events, pools) lives on
+    // the old devices, so they are torn down completely before the new ones are set up
+    shutdown_all();
+    for (int i = 0; i < count; i++) {
+        tl_ctx = &g_slots[i];
+        if (int rc = init_slot(devices[i], i)) {
+            char keep[sizeof g_error];
+            memcpy(keep, g_error, sizeof keep);
+            g_n_ctx = i + 1;
+            shutdown_all();
+            memcpy(g_error, keep, sizeof keep);
+            return rc;
+        }
+    }
+    g_n_ctx = count;
+    tl_ctx = &g_slots[0];
+    CUDA_TRY(cudaSetDevice(g_slots[0].device));
+    return 0;
+}
+
+int selab200_init(int device) { return selab200_init_devices(1, &device); }
+
+int selab200_device_count(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return g_n_ctx;
+}
+
+void selab200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    shutdown_all();
 }
 
 void *selab200_host_alloc(size_t bytes)
@@ -623,7 +723,7 @@ int selab200_encode_frames_device(const int16_t *d_pcm, uint32_t n_frames, uint3
                                   size_t workspace_bytes, void *stream)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
+    if (int rc = d_pcm ? require_ready_for(d_pcm) : require_ready())
         return rc;
     if (!d_pcm || !d_descs || !d_words || !d_words_used || !d_status || !d_workspace)
         return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
@@ -636,7 +736,7 @@ int selab200_decode_frames_device(const selab200_subframe_desc *d_descs, uint32_
                                   void *d_workspace, size_t workspace_bytes, void *stream)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
+    if (int rc = d_descs ? require_ready_for(d_descs) : require_ready())
         return rc;
     if (!d_descs || !d_words || !d_pcm_out || !d_status || !d_workspace)
         return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
@@ -657,7 +757,7 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
                                        int32_t *d_status, void *stream)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
+    if (int rc = d_descs ? require_ready_for(d_descs) : require_ready())
         return rc;
     if (!d_descs || !d_words || !d_residues || !d_status)
         return fail(SELAB200_ERR_ARGUMENT, "null device pointer");
@@ -707,6 +807,8 @@ int selab200_rice_decode_flagged(uint32_t *n_flagged)
     return 0;
 }
 
+} // extern "C"
+
 // Bytes of container in front of frame f when `words` Rice words precede it.
 static unsigned long long container_frame_byte(unsigned long long f, uint32_t channels, unsigned long long words)
 {
@@ -716,8 +818,12 @@ static unsigned long long container_frame_byte(unsigned long long f, uint32_t ch
 // The pipelined encoder over host buffers.  Two output forms: descriptors + word arena
 // (descs/words), or the byte-packed container (`container`, descs == words == nullptr) whose
 // device image lives in g.words.
+// `defer`: leave the word arena / container body on the device (g.words) instead of copying it out chunk by
+// chunk -- the multi-device driver places every device's block once the sizes of the blocks before it are known.
+// With `defer`, `container` is only a flag (any non-null value selects the byte-packed form).
 static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *descs,
-                       uint32_t *words, size_t words_capacity, size_t *words_used, uint8_t *container)
+                       uint32_t *words, size_t words_capacity, size_t *words_used, uint8_t *container,
+                       bool defer = false)
 {
     *words_used = 0;
     if (n_frames == 0)
@@ -767,6 +873,13 @@ static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
         const unsigned long long lo = g.h_totals[c], hi = g.h_totals[c + 1];
         if (hi > words_capacity || hi < lo)
             break; // capacity exceeded: reported through the status word below
+        if (defer) {
+            if (!container)
+                CUDA_TRY(cudaMemcpyAsync(descs + (size_t)f0 * channels, d_descs + (size_t)f0 * channels,
+                                         (size_t)nf * channels * sizeof(selab200_subframe_desc), cudaMemcpyDeviceToHost,
+                                         g.s_d2h));
+            continue;
+        }
         if (container) {
             const unsigned long long b0 = container_frame_byte(f0, channels, lo);
             const unsigned long long b1 = container_frame_byte(f0 + nf, channels, hi);
@@ -791,61 +904,9 @@ static int encode_host(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
     return 0;
 }
 
-int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
-                           selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
-                           size_t *words_used)
+static int decode_host(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
+                       const uint32_t *words, size_t n_words, int16_t *pcm_out)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
-        return rc;
-    if (!pcm || !descs || !words || !words_used)
-        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
-    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
-        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
-    return encode_host(pcm, n_frames, channels, descs, words, words_capacity, words_used, nullptr);
-}
-
-size_t selab200_container_bound(uint32_t n_frames, uint32_t channels)
-{
-    return (size_t)container_frame_byte(n_frames, channels, selab200_encode_words_bound(n_frames, channels));
-}
-
-int selab200_encode_container(const int16_t *pcm, uint32_t n_frames, uint32_t channels, uint32_t sample_rate,
-                              uint16_t bits_per_sample, uint8_t *container, size_t capacity, size_t *bytes_used)
-{
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
-        return rc;
-    if ((!pcm && n_frames) || !container || !bytes_used)
-        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
-    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
-        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
-    const unsigned long long fixed = container_frame_byte(n_frames, channels, 0);
-    *bytes_used = (size_t)fixed;
-    if (capacity < fixed)
-        return fail(SELAB200_ERR_CAPACITY, "container buffer too small: %zu bytes, need more than %llu", capacity, fixed);
-    // file::SelaFile::writeToFile, header part (src/file/sela_file.cpp:107-112)
-    const uint8_t header[15] = {'S', 'e', 'L', 'a',
-                                (uint8_t)sample_rate, (uint8_t)(sample_rate >> 8), (uint8_t)(sample_rate >> 16), (uint8_t)(sample_rate >> 24),
-                                (uint8_t)bits_per_sample, (uint8_t)(bits_per_sample >> 8), (uint8_t)channels,
-                                (uint8_t)n_frames, (uint8_t)(n_frames >> 8), (uint8_t)(n_frames >> 16), (uint8_t)(n_frames >> 24)};
-    memcpy(container, header, sizeof header);
-    size_t words_used = 0;
-    const int rc = encode_host(pcm, n_frames, channels, nullptr, nullptr, (size_t)((capacity - fixed) / 4), &words_used, container);
-    *bytes_used = (size_t)container_frame_byte(n_frames, channels, words_used);
-    return rc;
-}
-
-int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
-                           const uint32_t *words, size_t n_words, int16_t *pcm_out)
-{
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (int rc = require_ready())
-        return rc;
-    if (!descs || !pcm_out || (!words && n_words))
-        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
-    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
-        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     if (n_frames == 0)
         return 0;
     PipelineDrain drain;
@@ -903,6 +964,198 @@ int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frame
                                  nf * frame_bytes, cudaMemcpyDeviceToHost, g.s_d2h));
     }
     return read_status(g.s_d2h, d_status);
+}
+
+// ---- every initialised device at once ----------------------------------------------------------
+//
+// Frames are independent (src/sela/encoder.cpp:40-92 hands contiguous ranges of them to its threads); with more
+// than one device the host-buffer calls do the same with the devices: device d codes the contiguous block
+// frame_block(d) on a worker thread of its own, with its own context (streams, pools), straight from / into
+// disjoint ranges of the caller's buffers.  Only the encoder needs a second step: where a block's words land
+// depends on the sizes of the blocks before it, so the workers leave the words on their devices and the
+// calling thread copies them out (all devices at once) when every size is known, re-basing the descriptors'
+// offsets on the way.  The byte-packed container works the same way: a block's body is position independent
+// (DESIGN.md 6).
+struct DevicePart {
+    uint32_t f0 = 0, nf = 0;
+    int rc = 0;
+    size_t used = 0;
+    char err[sizeof g_error] = "";
+};
+
+static std::vector<DevicePart> device_parts(uint32_t n_frames)
+{
+    // n/D frames each, the last device takes the rest: the reference's thread split (src/sela/encoder.cpp:58-73)
+    std::vector<DevicePart> parts((size_t)g_n_ctx);
+    const uint32_t per = n_frames / (uint32_t)g_n_ctx;
+    for (int d = 0; d < g_n_ctx; d++) {
+        parts[d].f0 = per * d;
+        parts[d].nf = d == g_n_ctx - 1 ? n_frames - per * d : per;
+    }
+    return parts;
+}
+
+static bool use_all_devices(uint32_t n_frames)
+{
+    return g_n_ctx > 1 && n_frames >= 256u * (uint32_t)g_n_ctx;
+}
+
+template <typename F>
+static int run_on_devices(std::vector<DevicePart> &parts, F work)
+{
+    std::vector<std::thread> threads;
+    for (int d = 0; d < g_n_ctx; d++)
+        threads.emplace_back([&, d] {
+            tl_ctx = &g_slots[d];
+            DevicePart &p = parts[d];
+            cudaError_t e = cudaSetDevice(g.device);
+            p.rc = e == cudaSuccess ? work(p) : fail(SELAB200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g.device, cudaGetErrorString(e));
+            if (p.rc)
+                memcpy(p.err, g_error, sizeof p.err);
+        });
+    for (std::thread &t : threads)
+        t.join();
+    tl_ctx = &g_slots[0];
+    cudaSetDevice(g.device);
+    for (const DevicePart &p : parts)
+        if (p.rc) {
+            memcpy(g_error, p.err, sizeof g_error);
+            return p.rc;
+        }
+    return 0;
+}
+
+static int encode_all_devices(const int16_t *pcm, uint32_t n_frames, uint32_t channels, selab200_subframe_desc *descs,
+                              uint32_t *words, size_t words_capacity, size_t *words_used, uint8_t *container)
+{
+    std::vector<DevicePart> parts = device_parts(n_frames);
+    const size_t per_frame = (size_t)channels * kFrame;
+    const int rc = run_on_devices(parts, [&](DevicePart &p) {
+        return encode_host(pcm + p.f0 * per_frame, p.nf, channels, descs ? descs + (size_t)p.f0 * channels : nullptr, nullptr,
+                           selab200_encode_words_bound(p.nf, channels), &p.used, container, true);
+    });
+    size_t total = 0;
+    for (const DevicePart &p : parts)
+        total += p.used;
+    *words_used = total;
+    if (rc)
+        return rc;
+    if (total > words_capacity)
+        return fail(SELAB200_ERR_CAPACITY, "%s", status_text(SELAB200_ERR_CAPACITY));
+    size_t base = 0;
+    for (int d = 0; d < g_n_ctx; d++) { // every device's block goes out at once, each over its own link
+        tl_ctx = &g_slots[d];
+        const DevicePart &p = parts[d];
+        CUDA_TRY(cudaSetDevice(g.device));
+        if (container) {
+            const size_t body = (size_t)container_frame_byte(p.nf, channels, p.used) - kContainerHeaderBytes;
+            const size_t at = (size_t)container_frame_byte(p.f0, channels, base);
+            if (body)
+                CUDA_TRY(cudaMemcpyAsync(container + at, static_cast<uint8_t *>(g.words.ptr) + kContainerHeaderBytes, body,
+                                         cudaMemcpyDeviceToHost, g.s_d2h));
+        } else if (p.used) {
+            CUDA_TRY(cudaMemcpyAsync(words + base, g.words.ptr, p.used * 4, cudaMemcpyDeviceToHost, g.s_d2h));
+        }
+        base += p.used;
+    }
+    if (!container) { // meanwhile: descriptor offsets from block-local to file order
+        size_t b = 0;
+        for (const DevicePart &p : parts) {
+            if (b)
+                for (size_t i = (size_t)p.f0 * channels; i < (size_t)(p.f0 + p.nf) * channels; i++) {
+                    descs[i].refl_offset += b;
+                    descs[i].res_offset += b;
+                }
+            b += p.used;
+        }
+    }
+    int rc2 = 0;
+    for (int d = 0; d < g_n_ctx; d++) {
+        tl_ctx = &g_slots[d];
+        cudaSetDevice(g.device);
+        cudaError_t e = cudaStreamSynchronize(g.s_d2h);
+        if (e != cudaSuccess && !rc2)
+            rc2 = fail(SELAB200_ERR_CUDA, "download from device %d failed: %s", g.device, cudaGetErrorString(e));
+    }
+    tl_ctx = &g_slots[0];
+    cudaSetDevice(g.device);
+    return rc2;
+}
+
+static int decode_all_devices(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
+                              const uint32_t *words, size_t n_words, int16_t *pcm_out)
+{
+    std::vector<DevicePart> parts = device_parts(n_frames);
+    const size_t per_frame = (size_t)channels * kFrame;
+    return run_on_devices(parts, [&](DevicePart &p) {
+        return decode_host(descs + (size_t)p.f0 * channels, p.nf, channels, words, n_words, pcm_out + p.f0 * per_frame);
+    });
+}
+
+extern "C" {
+
+int selab200_encode_frames(const int16_t *pcm, uint32_t n_frames, uint32_t channels,
+                           selab200_subframe_desc *descs, uint32_t *words, size_t words_capacity,
+                           size_t *words_used)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!pcm || !descs || !words || !words_used)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    if (use_all_devices(n_frames))
+        return encode_all_devices(pcm, n_frames, channels, descs, words, words_capacity, words_used, nullptr);
+    return encode_host(pcm, n_frames, channels, descs, words, words_capacity, words_used, nullptr);
+}
+
+size_t selab200_container_bound(uint32_t n_frames, uint32_t channels)
+{
+    return (size_t)container_frame_byte(n_frames, channels, selab200_encode_words_bound(n_frames, channels));
+}
+
+int selab200_encode_container(const int16_t *pcm, uint32_t n_frames, uint32_t channels, uint32_t sample_rate,
+                              uint16_t bits_per_sample, uint8_t *container, size_t capacity, size_t *bytes_used)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if ((!pcm && n_frames) || !container || !bytes_used)
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    const unsigned long long fixed = container_frame_byte(n_frames, channels, 0);
+    *bytes_used = (size_t)fixed;
+    if (capacity < fixed)
+        return fail(SELAB200_ERR_CAPACITY, "container buffer too small: %zu bytes, need more than %llu", capacity, fixed);
+    // file::SelaFile::writeToFile, header part (src/file/sela_file.cpp:107-112)
+    const uint8_t header[15] = {'S', 'e', 'L', 'a',
+                                (uint8_t)sample_rate, (uint8_t)(sample_rate >> 8), (uint8_t)(sample_rate >> 16), (uint8_t)(sample_rate >> 24),
+                                (uint8_t)bits_per_sample, (uint8_t)(bits_per_sample >> 8), (uint8_t)channels,
+                                (uint8_t)n_frames, (uint8_t)(n_frames >> 8), (uint8_t)(n_frames >> 16), (uint8_t)(n_frames >> 24)};
+    memcpy(container, header, sizeof header);
+    size_t words_used = 0;
+    const int rc = use_all_devices(n_frames)
+                       ? encode_all_devices(pcm, n_frames, channels, nullptr, nullptr, (size_t)((capacity - fixed) / 4), &words_used, container)
+                       : encode_host(pcm, n_frames, channels, nullptr, nullptr, (size_t)((capacity - fixed) / 4), &words_used, container);
+    *bytes_used = (size_t)container_frame_byte(n_frames, channels, words_used);
+    return rc;
+}
+
+int selab200_decode_frames(const selab200_subframe_desc *descs, uint32_t n_frames, uint32_t channels,
+                           const uint32_t *words, size_t n_words, int16_t *pcm_out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = require_ready())
+        return rc;
+    if (!descs || !pcm_out || (!words && n_words))
+        return fail(SELAB200_ERR_ARGUMENT, "null pointer");
+    if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
+        return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
+    if (use_all_devices(n_frames))
+        return decode_all_devices(descs, n_frames, channels, words, n_words, pcm_out);
+    return decode_host(descs, n_frames, channels, words, n_words, pcm_out);
 }
 
 // ---- .sela container, decode side ----------------------------------------------------------

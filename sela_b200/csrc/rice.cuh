@@ -398,7 +398,8 @@ __device__ bool warp_rice_decode32(uint32_t *ring, const RiceLaneStream st)
                     st.out[n + e] = v[e];
         }
     }
-    return pos <= total * 32u;
+    // nothing to decode is never an overrun (a stream of zero words starts `skip` words into its first vector)
+    return count == 0 || pos <= total * 32u;
 }
 
 } // namespace selab200

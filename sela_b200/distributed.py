@@ -332,12 +332,12 @@ def scatter_frames_device(pcm_dev, n_frames, channels, src=0):
         for r in range(world):
             a, b = frame_block(n_frames, r, world)
             if r != src and b > a:
-                ops.append(dist.P2POp(dist.isend, pcm_dev[a * per:b * per], r))
+                ops.append(dist.P2POp(dist.isend, pcm_dev[a * per:b * per].view(torch.uint8), r))  # (NCCL has no int16)
         _p2p(ops)
         return pcm_dev[lo * per:hi * per]
     buf = torch.empty((hi - lo) * per, dtype=torch.int16, device=_dev())
     if hi > lo:
-        _p2p([dist.P2POp(dist.irecv, buf, src)])
+        _p2p([dist.P2POp(dist.irecv, buf.view(torch.uint8), src)])
     return buf
 
 
@@ -462,7 +462,7 @@ def decode_sharded_device(descs_dev, words_dev, n_frames, channels, root=0):
     def gather():
         if rank != root:
             if hi > lo:
-                _p2p([dist.P2POp(dist.isend, local, root)])
+                _p2p([dist.P2POp(dist.isend, local.view(torch.uint8), root)])
             return None
         out = torch.empty(n_frames * per, dtype=torch.int16, device=dev)
         ops = []
@@ -471,7 +471,7 @@ def decode_sharded_device(descs_dev, words_dev, n_frames, channels, root=0):
             if r == root:
                 out[a * per:b * per].copy_(local)
             elif b > a:
-                ops.append(dist.P2POp(dist.irecv, out[a * per:b * per], r))
+                ops.append(dist.P2POp(dist.irecv, out[a * per:b * per].view(torch.uint8), r))
         _p2p(ops)
         return out
     out, t_gather = _timed(gather, dev)

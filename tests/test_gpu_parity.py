@@ -402,3 +402,75 @@ def test_rice_decode_window_boundaries_for_every_k(O):
         assert np.array_equal(out[i, :len(us)], ref), k
         want = np.array([(u >> 1) ^ -(u & 1) for u in us], np.int64).astype(np.int32)
         assert np.array_equal(ref, want), k            # and the reference agrees with the textbook inverse
+
+
+def test_adversarial_frames_fit_their_slots(O):
+    """The batch encoder packs every analysis unit into a private 1 600-word slot (1 568 for the residues, 24.5
+    bits per sample) and refuses a frame that does not fit, where data::SelaSubFrame would carry up to 65 535
+    words (src/include/data/sela_sub_frame.hpp:30-44).  16-bit audio cannot get there: with k = 19 a stream costs
+    20 bits per sample plus (u >> 19), so 1 568 words need residues beyond 2^21, and a predictor fitted to the
+    frame itself does not amplify a 17-bit signal sixteen-fold.  Worst cases -- full-scale alternation, anti-
+    correlated stereo noise (17-bit difference), sign-flipping noise, chirps through the band edge, isolated
+    full-scale impulses -- must encode, equal the reference, and stay far inside the slot."""
+    rng = np.random.default_rng(99)
+    n = 2048
+    t = np.arange(n)
+    mono = {
+        "alternate_full": np.where(t % 2 == 0, 32767, -32768),
+        "alternate_pairs": np.where((t // 2) % 2 == 0, 32767, -32768),
+        "noise_full": rng.integers(-32768, 32768, n),
+        "sign_noise": rng.choice([-32768, 32767], n),
+        "chirp": np.round(32767 * np.sin(np.pi * t * t / (2.0 * n))).astype(np.int64),
+        "chirp_clipped": np.clip(np.round(60000 * np.sin(np.pi * t * t / (1.3 * n))), -32768, 32767).astype(np.int64),
+        "impulses": np.where(t % 257 == 0, 32767, 0) - np.where(t % 263 == 1, 32768, 0),
+        "step_train": np.where((t // 101) % 2 == 0, 32767, -32768),
+        "near_unstable": np.round(32767 * np.cos(np.pi * t * 0.999)).astype(np.int64),
+    }
+    frames = []
+    for name, a in mono.items():
+        a = np.asarray(a, np.int64).astype(np.int16)
+        frames.append(np.stack([a, a], axis=1))                                  # identical channels
+        frames.append(np.stack([a, (-a.astype(np.int32) - 1).clip(-32768, 32767).astype(np.int16)], axis=1))  # inverted: a 17-bit difference
+        frames.append(np.stack([a, rng.integers(-32768, 32768, n).astype(np.int16)], axis=1))
+    x = rng.integers(-32768, 32768, n).astype(np.int16)
+    frames.append(np.stack([x, (~x)], axis=1))                                   # anti-correlated full-scale noise
+    pcm = np.concatenate(frames).astype(np.int16)
+    d, w = sela_b200.encode_frames(pcm, 2)
+    d_ref, w_ref = O.encode_frames(pcm, 2)
+    assert d.tobytes() == d_ref.tobytes() and np.array_equal(w, w_ref)
+    assert int(d["res_words"].max()) <= 1344, int(d["res_words"].max())         # 21 bits per sample: k = 19 and one more bit
+    assert int(d["refl_words"].max()) <= 29
+    assert np.array_equal(sela_b200.decode_frames(d, w, 2), O.decode_frames(d_ref, w_ref, 2))
+    for ch in (1, 3):                                                            # the non-stereo staging path
+        m = np.concatenate([np.asarray(a, np.int64).astype(np.int16) for a in mono.values()])
+        m = m[: (m.size // (n * ch)) * n * ch].reshape(-1, ch)
+        dm, wm = sela_b200.encode_frames(m, ch)
+        dr, wr = O.encode_frames(m, ch)
+        assert dm.tobytes() == dr.tobytes() and np.array_equal(wm, wr)
+        assert int(dm["res_words"].max()) <= 1344
+
+
+def test_order_zero_subframe_at_any_word_offset(O):
+    """A subframe with no coefficient words (order 0, zero reflection words) decodes as a zero predictor in the
+    reference; the decoder must not call that an overrun, whatever 16-byte phase its (empty) stream sits at."""
+    rng = np.random.default_rng(3)
+    res = np.round(rng.laplace(0, 40, FRAME)).astype(np.int32)
+    k, nw, words = sela_b200.rice_encode(res[None, :], np.array([FRAME], np.uint32), words_stride=2048)
+    body = words[0, :nw[0]]
+    for pad in range(5):
+        arena = np.concatenate([np.full(pad, 0xFFFFFFFF, np.uint32), body])
+        d = np.zeros(1, _lib_desc())
+        d["lpc_order"] = 0
+        d["refl_words"] = 0
+        d["refl_offset"] = pad
+        d["res_rice_param"] = k[0]
+        d["res_words"] = nw[0]
+        d["samples"] = FRAME
+        d["res_offset"] = pad
+        out = sela_b200.decode_frames(d, arena, 1)
+        assert np.array_equal(out, res.astype(np.int16)), pad                    # zero predictor: samples = residues
+
+
+def _lib_desc():
+    from sela_b200 import _lib
+    return _lib.DESC_DTYPE

@@ -296,7 +296,7 @@ def sharded_block(args, rank, world, dev, dist):
         for i in range(distinct):
             bank[i * fs:(i + 1) * fs].copy_(torch.from_numpy(synth.sine_noise(44100, 2, n_frames=file_frames, seed=i).reshape(-1)))
     if dist:
-        dist.broadcast(bank, 0)
+        dist.broadcast(bank.view(torch.uint8), 0)      # (NCCL has no int16)
     mine = files_total // world + (1 if rank < files_total % world else 0)
     codec = DeviceCodec(file_frames, 2, device=dev.index)
     outp = torch.empty(fs, dtype=torch.int16, device=dev)

@@ -454,6 +454,24 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
         if (int rc2 = set_smem(k_rice_decode_vs<32, 16, 32>, smem))
             return rc2;
         k_rice_decode_vs<32, 16, 32><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom == 3) { // cooperative rings
+        constexpr size_t smem = vc_smem_bytes<32>();
+        if (int rc2 = set_smem(k_rice_decode_vc<16, 32>, smem))
+            return rc2;
+        k_rice_decode_vc<16, 32><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom >= 100 && geom < 108) { // ablations (measurement only): 100 + bit mask
+        constexpr size_t smem = vs_smem_bytes<64, 32>();
+        switch (geom - 100) {
+#define SELAB200_ABL(m)                                                                        \
+    case m:                                                                                    \
+        if (int rc2 = set_smem(k_rice_decode_vs<64, 16, 32, m>, smem))                         \
+            return rc2;                                                                        \
+        k_rice_decode_vs<64, 16, 32, m><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s); \
+        break;
+            SELAB200_ABL(1) SELAB200_ABL(2) SELAB200_ABL(3) SELAB200_ABL(4) SELAB200_ABL(5) SELAB200_ABL(6) SELAB200_ABL(7)
+#undef SELAB200_ABL
+        default: break;
+        }
     } else {
         constexpr size_t smem = vs_smem_bytes<64, 32>();
         if (int rc2 = set_smem(k_rice_decode_vs<64, 16, 32>, smem))

@@ -226,6 +226,163 @@ struct VsStream {
     }
 };
 
+// ------------------------------------------------------------------ the warp's rings, filled together --
+//
+// The per-lane cp.async of VsStream costs a 16-byte request to 32 different lines per instruction: at scale
+// the load/store unit replays of those requests, not the parse, bound the decoder (measured: the decoder
+// with the top-ups removed runs 2.3x faster).  Here the 32 rings of a warp are topped up COOPERATIVELY in
+// 128-byte segments: a ring is two segments of 32 words; a lane whose parser has left a segment puts its
+// row on a list, and eight lanes copy one row's next segment (8 x 16 bytes = one whole line) -- four rows,
+// four lines per instruction instead of 32.  All calls are warp-convergent.
+struct VsCoopMeta { // per warp, in shared memory
+    unsigned long long gbase[32]; // the row's stream from its 16-byte aligned base
+    int tbytes[32];               // bytes from gbase to the end of the stream (zeros behind)
+    uint32_t list[32];            // rows that want a segment: row | segment << 5
+};
+
+template <int ROUND, bool REVERSED>
+struct VsCoopStream {
+    static constexpr int kRing = 64, kSeg = 32;     // words
+    static constexpr uint32_t kMask = kRing * 4 - 1;
+    static_assert(ROUND <= 16, "a round must not outrun one segment's slack");
+    uint32_t row, rot;     // this lane's ring row (shared byte address, 256-aligned) and rotation
+    uint32_t rows0;        // shared byte address of the warp's row 0
+    VsCoopMeta *meta;
+    uint32_t pos, r0, r1, r2, wa;
+    uint32_t fs;           // next segment to request
+    uint32_t ls;           // segments below ls have landed (and are reversed)
+    uint32_t fs_prev;      // fs as it was after the previous boundary: those segments land with the next wait
+    uint32_t ce;           // words below ce are readable
+    uint32_t seg_limit;    // no segment beyond this one is ever needed
+
+    __device__ __forceinline__ uint32_t wb() const { return (pos >> 5) + 1; }
+    __device__ __forceinline__ uint32_t word_addr(uint32_t w) const { return row | ((4 * w + rot) & kMask); }
+    __device__ __forceinline__ uint32_t word(uint32_t w) const { return lds_u32(word_addr(w)); }
+    __device__ __forceinline__ void load_window()
+    {
+        const uint32_t w = wb();
+        r0 = word(w - 1);
+        r1 = word(w);
+        r2 = word(w + 1);
+        wa = 4 * (w + 1) + rot;
+    }
+    __device__ __forceinline__ void advance()
+    {
+        r0 = r1;
+        r1 = r2;
+        wa += 4;
+        r2 = lds_u32(row | (wa & kMask));
+    }
+    __device__ __forceinline__ void setup(uint32_t rows0_, VsCoopMeta *m, const uint4 *gvec, int total_bytes)
+    {
+        const int lane = lane_id();
+        rows0 = rows0_;
+        row = rows0_ + (uint32_t)lane * (kRing * 4);
+        rot = (16u * lane) & kMask;
+        meta = m;
+        m->gbase[lane] = (unsigned long long)reinterpret_cast<uintptr_t>(gvec);
+        m->tbytes[lane] = total_bytes;
+        seg_limit = ((uint32_t)total_bytes >> 7) + 2;
+        __syncwarp();
+    }
+    // Copy one segment for every lane with `want` (its `fs`); does not commit.
+    __device__ __forceinline__ void fill(bool want)
+    {
+        const int lane = lane_id();
+        const uint32_t mask = __ballot_sync(kFull, want);
+        if (mask == 0)
+            return;
+        if (want)
+            meta->list[__popc(mask & ((1u << lane) - 1u))] = (uint32_t)lane | (fs << 5);
+        __syncwarp();
+        const int n = __popc(mask);
+        for (int it = 0; it * 4 < n; it++) { // four rows per instruction, eight lanes x 16 bytes each
+            const int idx = it * 4 + (lane >> 3);
+            if (idx < n) {
+                const uint32_t e = meta->list[idx];
+                const uint32_t r = e & 31u, seg = e >> 5;
+                const uint32_t off = seg * 128u + 16u * (lane & 7);
+                const int rem = meta->tbytes[r] - (int)off;
+                const uint32_t sz = rem <= 0 ? 0u : rem < 16 ? (uint32_t)rem : 16u;
+                const char *src = reinterpret_cast<const char *>((uintptr_t)meta->gbase[r]) + (sz ? off : 0u);
+                const uint32_t dst = (rows0 + r * (kRing * 4)) | ((off + 16u * r) & kMask);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+            }
+        }
+        __syncwarp(); // the list is free again
+    }
+    __device__ __forceinline__ void reverse_segment(uint32_t seg) const
+    {
+#pragma unroll
+        for (int v = 0; v < 8; v += 2) {
+            const uint32_t a = row | ((128 * seg + 16 * v + rot) & kMask), b = row | ((128 * seg + 16 * v + 16 + rot) & kMask);
+            uint32_t x0, y0, z0, w0, x1, y1, z1, w1;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(z0), "=r"(w0) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x1), "=r"(y1), "=r"(z1), "=r"(w1) : "r"(b));
+            x0 = __brev(x0), y0 = __brev(y0), z0 = __brev(z0), w0 = __brev(w0);
+            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x0), "r"(y0), "r"(z0), "r"(w0), "r"(a) : "memory");
+            x1 = __brev(x1), y1 = __brev(y1), z1 = __brev(z1), w1 = __brev(w1);
+            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x1), "r"(y1), "r"(z1), "r"(w1), "r"(b) : "memory");
+        }
+    }
+    __device__ __forceinline__ void retire(uint32_t upto)
+    {
+        while (ls < upto) {
+            if (REVERSED)
+                reverse_segment(ls);
+            ls++;
+        }
+        ce = kSeg * ls;
+    }
+    // (Re)start the lanes with `want` at bit p.  Convergent; every earlier copy of the warp must have landed
+    // (cp_async_wait<0> + __syncwarp by the caller if unsure).
+    __device__ __forceinline__ void prime(uint32_t p, bool want)
+    {
+        if (want) {
+            pos = p;
+            fs = ls = (wb() - 1) >> 5;
+        }
+        fill(want);
+        if (want)
+            fs++;
+        fill(want);
+        if (want)
+            fs++;
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (want) {
+            retire(fs);
+            fs_prev = fs;
+            load_window();
+        }
+    }
+    // Top-up for the lanes with `want`.  Convergent.
+    __device__ __forceinline__ void boundary(bool want)
+    {
+        // segment fs goes where segment fs - 2 was: free once the parser (r0 = word wb - 1) has left it
+        const bool ready = want && kSeg * (fs - 1) <= wb() - 1 && fs <= seg_limit;
+        fill(ready);
+        if (ready)
+            fs++;
+        cp_async_commit();
+        cp_async_wait<1>(); // what the previous boundary requested has landed ...
+        __syncwarp();       // ... for every lane of the warp
+        if (want)
+            retire(fs_prev);
+        // A round reads at most ROUND + 2 words past r1.  A parser that entered its last landed segment late in
+        // a dense stretch may need the segment requested just now: wait for it (rare).
+        const bool tight = want && ce < wb() + ROUND + 3;
+        if (__any_sync(kFull, tight)) {
+            cp_async_wait<0>();
+            __syncwarp();
+            if (want)
+                retire(fs);
+        }
+        fs_prev = fs;
+    }
+};
+
 // ------------------------------------------------------------------ split index --
 //
 // No payload is read here, so the words stay as they lie in memory (stream bit b = bit b%32 of word b/32):
@@ -573,7 +730,9 @@ __device__ __noinline__ bool vs_slow_round(const VsRing<RING> rg, uint32_t ce, u
     return true;
 }
 
-template <int RING, int ROUND, int TILE>
+// ABLATE (measurement only, tools/rice_ablation.py; results are wrong): 1 = no global stores, 2 = no ring
+// top-ups after the first fill, 4 = no in-place reversal.
+template <int RING, int ROUND, int TILE, int ABLATE = 0>
 __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p, int log2s)
 {
     static_assert(TILE % ROUND == 0 && TILE % 4 == 0 && ROUND % 4 == 0 && TILE <= 32, "tile geometry");
@@ -613,7 +772,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p.words + (ok ? d.res_offset : 0));
     const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
     const uint32_t total = ok && d.res_words ? (uint32_t)d.res_words + skip : 0u;
-    using Stream = VsStream<RING, ROUND, true>;
+    using Stream = VsStream<RING, ROUND, !(ABLATE & 4)>;
     Stream s;
     s.rg.row = smem0 + pad + (uint32_t)(warp * 32 + lane) * (RING * 4);
     s.rg.rot = (16u * lane) & (RING * 4 - 1);
@@ -633,7 +792,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
     const uint32_t c_pn = kp1 + 31;
 #pragma unroll 1
     for (uint32_t r = 0; r < n_rounds; r++) {
-        if (r && !dead)
+        if (r && !dead && !(ABLATE & 2))
             s.boundary();
         uint32_t pos_s = s.pos;
         int mn = 31; // lowest FLO result of the round; below k: a symbol longer than the window
@@ -657,7 +816,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
             }
             *reinterpret_cast<int4 *>(trow + e4) = make_int4(val[0], val[1], val[2], val[3]);
         }
-        if (mn < (int)k && !dead) { // a symbol longer than the window: redo the round with the general parser
+        if (mn < (int)k && !dead && !(ABLATE & 6)) { // a symbol longer than the window: redo the round with the general parser
             if (vs_slow_round<RING>(s.rg, s.ce, &pos_s, k, trow, ROUND)) {
                 s.pos = pos_s;
                 s.load_window();
@@ -666,6 +825,140 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
             }
         }
         // ---- a full tile: TILE symbols per lane leave as row segments of 4*TILE bytes ----
+        if (r % (TILE / ROUND) == TILE / ROUND - 1) {
+            __syncwarp();
+            int32_t *dst = out_warp + (size_t)(r / (TILE / ROUND)) * TILE + (lane % kRowLanes) * 4;
+#pragma unroll
+            for (int it = 0; it < 32 / kRowsPerIt; it++) {
+                const int row = kRowsPerIt * it + lane / kRowLanes;
+                if ((row_mask >> row) & 1u) {
+                    const int4 q = *reinterpret_cast<const int4 *>(tile + row * kTilePitch + (lane % kRowLanes) * 4);
+                    if (!(ABLATE & 1) || q.x == 0x7fffffff)
+                        *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
+    if (exists && store_row) {
+        bool bad = dead;
+        if (ok) {
+            if (expect_end != kNoSplit)
+                bad |= s.pos - 32 * skip != expect_end;
+            else
+                bad |= s.pos > total * 32;
+        }
+        if (bad && !(ABLATE & 6))
+            p.flags[st] = 1u; // (several parts may say so: idempotent)
+    }
+}
+
+// The decoder on the cooperative rings (VsCoopStream): same parse, same tile, warp-wide top-ups.
+template <int RING>
+__device__ __noinline__ bool vc_slow_round(uint32_t row, uint32_t rot, uint32_t ce, uint32_t *pos, uint32_t k, int32_t *dst, int count)
+{
+    VsRing<RING> rg;
+    rg.row = row;
+    rg.rot = rot;
+    rg.gvec = nullptr;
+    rg.total_bytes = 0;
+    return vs_slow_round<RING>(rg, ce, pos, k, dst, count);
+}
+
+template <int ROUND, int TILE>
+__global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p, int log2s)
+{
+    using Stream = VsCoopStream<ROUND, true>;
+    constexpr int RING = Stream::kRing;
+    static_assert(TILE % ROUND == 0 && TILE % 4 == 0 && ROUND % 4 == 0 && TILE <= 32, "tile geometry");
+    constexpr int kTilePitch = TILE + 4;
+    constexpr int kRowLanes = TILE / 4;
+    constexpr int kRowsPerIt = 32 / kRowLanes;
+    extern __shared__ __align__(16) unsigned char vc_smem[];
+    const int lane = lane_id(), warp = warp_id();
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(vc_smem);
+    const uint32_t pad = (RING * 4 - (smem0 & (RING * 4 - 1))) & (RING * 4 - 1);
+    int32_t *tile = reinterpret_cast<int32_t *>(vc_smem + pad + kVsWarps * 32 * RING * 4) + warp * 32 * kTilePitch;
+    VsCoopMeta *meta = reinterpret_cast<VsCoopMeta *>(vc_smem + pad + kVsWarps * 32 * RING * 4 + kVsWarps * 32 * kTilePitch * 4) + warp;
+
+    const uint32_t S = 1u << log2s, part = (uint32_t)kFrame >> log2s;
+    const uint32_t v0 = (blockIdx.x * kVsWarps + warp) * 32;
+    const uint32_t v = v0 + lane, st = v >> log2s, l = v & (S - 1);
+    const bool exists = st < p.n_sub;
+    selab200_subframe_desc d;
+    memset(&d, 0, sizeof d);
+    if (exists)
+        d = p.descs[st];
+    bool ok = exists && rice_desc_ok(d, p.channels, p.n_words);
+    if (exists && !ok && l == 0)
+        raise_status(p.status, SELAB200_ERR_BITSTREAM);
+    const bool store_row = ok; // rows of flagged streams may hold garbage: the general kernel rewrites them
+    uint32_t sb = 0, expect_end = kNoSplit;
+    if (ok && S > 1) {
+        const uint32_t *tb = p.table + (size_t)st * (S - 1);
+        if (tb[0] == kNoSplit) {
+            ok = false; // not split: the general kernel decodes it
+        } else {
+            if (l > 0)
+                sb = tb[l - 1];
+            if (l < S - 1)
+                expect_end = tb[l];
+        }
+    }
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p.words + (ok ? d.res_offset : 0));
+    const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
+    const uint32_t total = ok && d.res_words ? (uint32_t)d.res_words + skip : 0u;
+    Stream s;
+    s.setup(smem0 + pad + (uint32_t)(warp * 32) * (RING * 4), meta, reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15), (int)(total * 4));
+    const uint32_t k = ok ? d.res_rice_param : 0u, kp1 = k + 1, kk = 32 - k, kpow = 1u << k;
+    const uint32_t row_mask = __ballot_sync(kFull, store_row);
+
+    uint32_t p0 = sb + 32 * skip;
+    if (p0 > total * 32 + 64)
+        p0 = total * 32 + 64; // a nonsense table entry: parse zeros, fail the end check
+    s.prime(p0, true);
+    bool dead = false;
+
+    int32_t *out_warp = p.out + (size_t)v0 * part;
+    const uint32_t n_rounds = part / ROUND;
+    const uint32_t c_pn = kp1 + 31;
+#pragma unroll 1
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        if (r)
+            s.boundary(!dead);
+        uint32_t pos_s = s.pos;
+        int mn = 31; // lowest FLO result of the round; below k: a symbol longer than the window
+        int32_t *trow = tile + lane * kTilePitch + (r % (TILE / ROUND)) * ROUND;
+#pragma unroll
+        for (int e4 = 0; e4 < ROUND; e4 += 4) {
+            int32_t val[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t win = __funnelshift_l(s.r1, s.r0, s.pos);
+                const uint32_t f = bfind_u32(~win);   // 31 - ones; 0xffffffff: the window is all ones
+                const uint32_t pn = s.pos + c_pn - f; // pos + ones + 1 + k
+                mn = min(mn, (int)f);
+                const uint32_t ones = 31 - f;
+                const uint32_t t = __funnelshift_lc(0u, win, ones + 1);
+                const uint32_t pay = __funnelshift_rc(t, 0u, kk);
+                val[e] = unzigzag3(ones * kpow + pay);
+                if ((s.pos ^ pn) >= 32u)
+                    s.advance();
+                s.pos = pn;
+            }
+            *reinterpret_cast<int4 *>(trow + e4) = make_int4(val[0], val[1], val[2], val[3]);
+        }
+        if (mn < (int)k && !dead) { // a symbol longer than the window: redo the round with the general parser
+            if (vc_slow_round<RING>(s.row, s.rot, s.ce, &pos_s, k, trow, ROUND)) {
+                s.pos = pos_s;
+                s.load_window();
+            } else {
+                dead = true;
+            }
+        }
+        if (dead)
+            s.pos = pos_s; // parked: its ring is not topped up any more
         if (r % (TILE / ROUND) == TILE / ROUND - 1) {
             __syncwarp();
             int32_t *dst = out_warp + (size_t)(r / (TILE / ROUND)) * TILE + (lane % kRowLanes) * 4;
@@ -690,8 +983,14 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vs(RiceVsParams p
                 bad |= s.pos > total * 32;
         }
         if (bad)
-            p.flags[st] = 1u; // (several parts may say so: idempotent)
+            p.flags[st] = 1u;
     }
+}
+
+template <int TILE>
+constexpr size_t vc_smem_bytes()
+{
+    return 64 * 4 + (size_t)kVsWarps * 32 * 64 * 4 + (size_t)kVsWarps * 32 * (TILE + 4) * 4 + kVsWarps * sizeof(VsCoopMeta);
 }
 
 template <int RING, int TILE>

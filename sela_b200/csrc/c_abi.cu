@@ -379,11 +379,11 @@ int rice_split_log2(size_t n_sub)
             l++;
         return l;
     }
-    // Measured on B200 (profiles/r02_rice_decode_roofline.json): from about 20 000 streams up one lane per stream
+    // Measured on B200 (profiles/r02_rice_decode_roofline.json): from about 12 000 streams up one lane per stream
     // (S = 1) through k_rice_decode_vs is fastest -- the two split passes cost more than the extra warps bring
     // once every SM has a few warps of its own; below that the machine is starved and cutting the streams
     // wins (500 streams: S = 16 is 3.5x the first-generation kernel, 8 000 streams: S = 8 is 1.9x).
-    if (n_sub >= 20000)
+    if (n_sub >= 12000)
         return 0;
     int l = 0;
     while (l < 4 && (n_sub << l) < (size_t)40000)
@@ -440,8 +440,9 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
         return rc;
     const size_t n_vs = n_sub << log2s;
     const unsigned vs_blocks = (unsigned)((n_vs + 32 * kVsWarps - 1) / (32 * kVsWarps));
-    // geometry: 0 = deep ring, full-line stores (fewest instructions); 1 = half the shared memory, twice the warps
-    int geom = 0;
+    // geometry: 3 = rings filled cooperatively, 128-byte segments (default: fastest at every batch size measured);
+    // 0 = per-lane cp.async rings; 1, 2 = the same with half the shared memory; 100+ = ablations (tools/rice_ablation.sh)
+    int geom = 3;
     if (const char *env = std::getenv("SELAB200_RICE_GEOM"))
         geom = std::atoi(env);
     if (geom == 1) {

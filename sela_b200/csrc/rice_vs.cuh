@@ -240,6 +240,20 @@ struct VsCoopMeta { // per warp, in shared memory
     uint32_t list[32];            // rows that want a segment: row | segment << 5
 };
 
+// add / subtract on the FMA pipe (IMAD.IADD): the parser is bound by the ALU pipe (shifts, logic, compares)
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t fma_sub(uint32_t a, uint32_t b) // a - b
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(b), "r"(a));
+    return d;
+}
+
 template <int ROUND, bool REVERSED>
 struct VsCoopStream {
     static constexpr int kRing = 64, kSeg = 32;     // words
@@ -270,7 +284,7 @@ struct VsCoopStream {
     {
         r0 = r1;
         r1 = r2;
-        wa += 4;
+        wa = fma_add(wa, 4);
         r2 = lds_u32(row | (wa & kMask));
     }
     __device__ __forceinline__ void setup(uint32_t rows0_, VsCoopMeta *m, const uint4 *gvec, int total_bytes)
@@ -936,11 +950,11 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const uint32_t win = __funnelshift_l(s.r1, s.r0, s.pos);
-                const uint32_t f = bfind_u32(~win);   // 31 - ones; 0xffffffff: the window is all ones
-                const uint32_t pn = s.pos + c_pn - f; // pos + ones + 1 + k
+                const uint32_t f = bfind_u32(~win);           // 31 - ones; 0xffffffff: the window is all ones
+                const uint32_t pn = fma_sub(s.pos + c_pn, f); // pos + ones + 1 + k (the adds run on the FMA pipe)
                 mn = min(mn, (int)f);
-                const uint32_t ones = 31 - f;
-                const uint32_t t = __funnelshift_lc(0u, win, ones + 1);
+                const uint32_t ones = fma_sub(31u, f);
+                const uint32_t t = __funnelshift_lc(0u, win, fma_sub(32u, f));
                 const uint32_t pay = __funnelshift_rc(t, 0u, kk);
                 val[e] = unzigzag3(ones * kpow + pay);
                 if ((s.pos ^ pn) >= 32u)

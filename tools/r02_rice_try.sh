@@ -1,9 +1,8 @@
 #!/bin/bash
 TAG=${1:-r02m}
 mkdir -p gpurun_out
-SELAB200_RICE_GEOM=3 timeout 900 python -m pytest tests/test_rice_split.py -x -q 2>&1 | tail -6
-for G in 0 3; do
-  echo "== geometry B=$G"
-  SELAB200_RICE_GEOM=$G timeout 600 python tools/rice_decode_roofline.py 16 --tiles 1,4,16 --splits 1 --out gpurun_out/rice_roofline_${TAG}_b${G}.json 2>&1 | grep streams
-  SELAB200_RICE_GEOM=$G timeout 600 python tools/rice_decode_roofline.py 1 --tiles 1 --splits 2,4,8 --out gpurun_out/rice_roofline_${TAG}_split_b${G}.json 2>&1 | grep streams
+timeout 900 python -m pytest tests/test_rice_split.py tests/test_gpu_parity.py -x -q 2>&1 | tail -6
+timeout 600 python tools/rice_decode_roofline.py 48 --tiles 1,4,16,48 --splits auto --out gpurun_out/rice_roofline_${TAG}.json 2>&1 | grep streams
+for F in 250 1000 4000 8000; do
+  timeout 300 python tools/rice_decode_roofline.py 1 --tiles 1 --frames $F --splits 0,1,auto --out gpurun_out/rice_small_${TAG}_f$F.json 2>&1 | grep streams
 done

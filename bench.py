@@ -244,6 +244,7 @@ def sharded_block(args, rank, world, dev, dist):
     if dist:
         (d_all, w_all), t_enc = sd.encode_sharded_device(pcm_dev, n_frames, ch, root=0)
         (d_all2, w_all2), t_enc2 = sd.encode_sharded_device(pcm_dev, n_frames, ch, root=0)   # second pass: warm
+        sd.decode_sharded_device(d_all2, w_all2, n_frames, ch, root=0)                        # first pass: NCCL sets its peer connections up
         pcm_back, t_dec = sd.decode_sharded_device(d_all2, w_all2, n_frames, ch, root=0)
     else:
         t_enc2 = t_dec = None

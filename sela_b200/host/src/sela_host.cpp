@@ -12,6 +12,8 @@
 #include <atomic>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <vector>
 #include <thread>
 
 #include "sela_api.hpp"
@@ -39,8 +41,31 @@ void ensure_device()
     std::lock_guard<std::mutex> lock(m);
     if (ready)
         return;
-    const char *env = std::getenv("SELAB200_DEVICE");
-    check(selab200_init(env ? std::atoi(env) : 0));
+    // SELAB200_DEVICES = "0,1,2,3" (or "all"): the batch calls then cut the frames into one block per device;
+    // SELAB200_DEVICE = n: one device (default: device 0 -- a CUDA context per GPU is not free, and one
+    // ten-minute file is a few milliseconds of work).
+    if (const char *list = std::getenv("SELAB200_DEVICES")) {
+        std::vector<int> ids;
+        if (std::string(list) == "all") {
+            int dev = 0;
+            while (dev < 16 && selab200_init(dev) == SELAB200_OK) // probe how many there are
+                ids.push_back(dev++);
+        } else {
+            for (const char *c = list; *c;) {
+                ids.push_back(std::atoi(c));
+                while (*c && *c != ',')
+                    c++;
+                if (*c == ',')
+                    c++;
+            }
+        }
+        if (ids.empty())
+            ids.push_back(0);
+        check(selab200_init_devices((int)ids.size(), ids.data()));
+    } else {
+        const char *env = std::getenv("SELAB200_DEVICE");
+        check(selab200_init(env ? std::atoi(env) : 0));
+    }
     ready = true;
 }
 

@@ -460,6 +460,34 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
         if (int rc2 = set_smem(k_rice_decode_vc<16, 32>, smem))
             return rc2;
         k_rice_decode_vc<16, 32><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom == 4) { // cooperative rings, half tile (more warps per SM)
+        constexpr size_t smem = vc_smem_bytes<16>();
+        if (int rc2 = set_smem(k_rice_decode_vc<16, 16>, smem))
+            return rc2;
+        k_rice_decode_vc<16, 16><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom == 5) { // cooperative rings, 256-byte row segments on the way out
+        constexpr size_t smem = vc_smem_bytes<64>();
+        if (int rc2 = set_smem(k_rice_decode_vc<16, 64>, smem))
+            return rc2;
+        k_rice_decode_vc<16, 64><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom == 6) { // 512-byte row segments
+        constexpr size_t smem = vc_smem_bytes<128>();
+        if (int rc2 = set_smem(k_rice_decode_vc<16, 128>, smem))
+            return rc2;
+        k_rice_decode_vc<16, 128><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
+    } else if (geom >= 200 && geom < 216) { // ablations of the cooperative decoder: 200 + bit mask (8: no copy instruction)
+        constexpr size_t smem = vc_smem_bytes<32>();
+        switch (geom - 200) {
+#define SELAB200_ABL(m)                                                                    \
+    case m:                                                                                \
+        if (int rc2 = set_smem(k_rice_decode_vc<16, 32, m>, smem))                         \
+            return rc2;                                                                    \
+        k_rice_decode_vc<16, 32, m><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s); \
+        break;
+            SELAB200_ABL(1) SELAB200_ABL(2) SELAB200_ABL(3) SELAB200_ABL(4) SELAB200_ABL(5) SELAB200_ABL(6) SELAB200_ABL(7) SELAB200_ABL(8) SELAB200_ABL(12)
+#undef SELAB200_ABL
+        default: break;
+        }
     } else if (geom >= 100 && geom < 108) { // ablations (measurement only): 100 + bit mask
         constexpr size_t smem = vs_smem_bytes<64, 32>();
         switch (geom - 100) {

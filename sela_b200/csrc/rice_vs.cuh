@@ -235,9 +235,10 @@ struct VsStream {
 // row on a list, and eight lanes copy one row's next segment (8 x 16 bytes = one whole line) -- four rows,
 // four lines per instruction instead of 32.  All calls are warp-convergent.
 struct VsCoopMeta { // per warp, in shared memory
-    unsigned long long gbase[32]; // the row's stream from its 16-byte aligned base
-    int tbytes[32];               // bytes from gbase to the end of the stream (zeros behind)
-    uint32_t list[32];            // rows that want a segment: row | segment << 5
+    // rows that want a segment, each entry written by the row's owner and read by the eight lanes that copy
+    // it: x, y = source address of the segment; z = bytes of stream left from there (<= 0: zeros only);
+    // w = shared byte address of the segment's first word in the row's ring
+    uint4 list[32];
 };
 
 // add / subtract on the FMA pipe (IMAD.IADD): the parser is bound by the ALU pipe (shifts, logic, compares)
@@ -254,7 +255,7 @@ __device__ __forceinline__ uint32_t fma_sub(uint32_t a, uint32_t b) // a - b
     return d;
 }
 
-template <int ROUND, bool REVERSED>
+template <int ROUND, bool REVERSED, bool NOCOPY = false>
 struct VsCoopStream {
     static constexpr int kRing = 64, kSeg = 32;     // words
     static constexpr uint32_t kMask = kRing * 4 - 1;
@@ -262,10 +263,12 @@ struct VsCoopStream {
     uint32_t row, rot;     // this lane's ring row (shared byte address, 256-aligned) and rotation
     uint32_t rows0;        // shared byte address of the warp's row 0
     VsCoopMeta *meta;
+    unsigned long long gbase; // this lane's stream from its 16-byte aligned base
+    int total_bytes;          // bytes from gbase to the end of the stream (zeros behind)
     uint32_t pos, r0, r1, r2, wa;
     uint32_t fs;           // next segment to request
     uint32_t ls;           // segments below ls have landed (and are reversed)
-    uint32_t fs_prev;      // fs as it was after the previous boundary: those segments land with the next wait
+    uint32_t seq, req_seq; // boundary counter; the boundary at which this lane's outstanding segment was requested
     uint32_t ce;           // words below ce are readable
     uint32_t seg_limit;    // no segment beyond this one is ever needed
 
@@ -294,10 +297,9 @@ struct VsCoopStream {
         row = rows0_ + (uint32_t)lane * (kRing * 4);
         rot = (16u * lane) & kMask;
         meta = m;
-        m->gbase[lane] = (unsigned long long)reinterpret_cast<uintptr_t>(gvec);
-        m->tbytes[lane] = total_bytes;
+        gbase = (unsigned long long)reinterpret_cast<uintptr_t>(gvec);
+        this->total_bytes = total_bytes;
         seg_limit = ((uint32_t)total_bytes >> 7) + 2;
-        __syncwarp();
     }
     // Copy one segment for every lane with `want` (its `fs`); does not commit.
     __device__ __forceinline__ void fill(bool want)
@@ -306,21 +308,27 @@ struct VsCoopStream {
         const uint32_t mask = __ballot_sync(kFull, want);
         if (mask == 0)
             return;
-        if (want)
-            meta->list[__popc(mask & ((1u << lane) - 1u))] = (uint32_t)lane | (fs << 5);
+        if (want) {
+            const uint32_t off = fs * 128u;
+            const int rem = total_bytes - (int)off;
+            const unsigned long long src = gbase + (rem > 0 ? off : 0u);
+            meta->list[__popc(mask & ((1u << lane) - 1u))] =
+                make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)rem, row | ((off + rot) & kMask));
+        }
         __syncwarp();
         const int n = __popc(mask);
+        const uint32_t piece = 16u * (lane & 7);
         for (int it = 0; it * 4 < n; it++) { // four rows per instruction, eight lanes x 16 bytes each
             const int idx = it * 4 + (lane >> 3);
             if (idx < n) {
-                const uint32_t e = meta->list[idx];
-                const uint32_t r = e & 31u, seg = e >> 5;
-                const uint32_t off = seg * 128u + 16u * (lane & 7);
-                const int rem = meta->tbytes[r] - (int)off;
+                const uint4 e = meta->list[idx];
+                const int rem = (int)e.z - (int)piece;
                 const uint32_t sz = rem <= 0 ? 0u : rem < 16 ? (uint32_t)rem : 16u;
-                const char *src = reinterpret_cast<const char *>((uintptr_t)meta->gbase[r]) + (sz ? off : 0u);
-                const uint32_t dst = (rows0 + r * (kRing * 4)) | ((off + 16u * r) & kMask);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                const unsigned long long src = (((unsigned long long)e.y << 32) | e.x) + (sz ? piece : 0u);
+                // the segment may wrap inside the row only at its end: it starts on a 128-byte boundary of the rotated row
+                const uint32_t dst = (e.w & ~kMask) | ((e.w + piece) & kMask);
+                if (!NOCOPY || sz == 77u)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
             }
         }
         __syncwarp(); // the list is free again
@@ -348,10 +356,11 @@ struct VsCoopStream {
         }
         ce = kSeg * ls;
     }
-    // (Re)start the lanes with `want` at bit p.  Convergent; every earlier copy of the warp must have landed
-    // (cp_async_wait<0> + __syncwarp by the caller if unsure).
+    // (Re)start the lanes with `want` at bit p.  Convergent.
     __device__ __forceinline__ void prime(uint32_t p, bool want)
     {
+        cp_async_wait<0>();
+        __syncwarp();
         if (want) {
             pos = p;
             fs = ls = (wb() - 1) >> 5;
@@ -367,33 +376,45 @@ struct VsCoopStream {
         __syncwarp();
         if (want) {
             retire(fs);
-            fs_prev = fs;
             load_window();
         }
+        seq = 0;
+        req_seq = 0;
     }
     // Top-up for the lanes with `want`.  Convergent.
+    // A segment is requested as soon as the parser has left the slot it goes to, but it is only waited for when
+    // a parser is about to run out of landed words -- typically two or three rounds later, so the copy has had
+    // that long to arrive (cp.async groups complete in order: waiting for "all but the last N groups" is waiting
+    // for a request N boundaries old).
     __device__ __forceinline__ void boundary(bool want)
     {
+        seq++;
         // segment fs goes where segment fs - 2 was: free once the parser (r0 = word wb - 1) has left it
-        const bool ready = want && kSeg * (fs - 1) <= wb() - 1 && fs <= seg_limit;
+        const uint32_t w = wb();
+        const bool ready = want && kSeg * (fs - 1) <= w - 1 && fs <= seg_limit;
         fill(ready);
-        if (ready)
+        if (ready) {
             fs++;
-        cp_async_commit();
-        cp_async_wait<1>(); // what the previous boundary requested has landed ...
-        __syncwarp();       // ... for every lane of the warp
-        if (want)
-            retire(fs_prev);
-        // A round reads at most ROUND + 2 words past r1.  A parser that entered its last landed segment late in
-        // a dense stretch may need the segment requested just now: wait for it (rare).
-        const bool tight = want && ce < wb() + ROUND + 3;
-        if (__any_sync(kFull, tight)) {
-            cp_async_wait<0>();
+            req_seq = seq;
+        }
+        cp_async_commit(); // one group per boundary, empty or not
+        // a round reads at most ROUND + 2 words past r1
+        const bool need = want && ls < fs && ce < w + ROUND + 3;
+        const uint32_t age = __reduce_min_sync(kFull, need ? seq - req_seq : 99u);
+        if (age != 99u) {
+            if (age == 0)
+                cp_async_wait<0>();
+            else if (age == 1)
+                cp_async_wait<1>();
+            else if (age == 2)
+                cp_async_wait<2>();
+            else
+                cp_async_wait<3>();
             __syncwarp();
-            if (want)
+            const uint32_t landed = age > 3 ? 3 : age;
+            if (want && ls < fs && seq - req_seq >= landed)
                 retire(fs);
         }
-        fs_prev = fs;
     }
 };
 
@@ -880,12 +901,12 @@ __device__ __noinline__ bool vc_slow_round(uint32_t row, uint32_t rot, uint32_t 
     return vs_slow_round<RING>(rg, ce, pos, k, dst, count);
 }
 
-template <int ROUND, int TILE>
+template <int ROUND, int TILE, int ABLATE = 0>
 __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p, int log2s)
 {
-    using Stream = VsCoopStream<ROUND, true>;
+    using Stream = VsCoopStream<ROUND, !(ABLATE & 4), (ABLATE & 8) != 0>;
     constexpr int RING = Stream::kRing;
-    static_assert(TILE % ROUND == 0 && TILE % 4 == 0 && ROUND % 4 == 0 && TILE <= 32, "tile geometry");
+    static_assert(TILE % ROUND == 0 && TILE % 4 == 0 && ROUND % 4 == 0 && TILE <= 128, "tile geometry");
     constexpr int kTilePitch = TILE + 4;
     constexpr int kRowLanes = TILE / 4;
     constexpr int kRowsPerIt = 32 / kRowLanes;
@@ -939,7 +960,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
     const uint32_t c_pn = kp1 + 31;
 #pragma unroll 1
     for (uint32_t r = 0; r < n_rounds; r++) {
-        if (r)
+        if (r && !(ABLATE & 2))
             s.boundary(!dead);
         uint32_t pos_s = s.pos;
         int mn = 31; // lowest FLO result of the round; below k: a symbol longer than the window
@@ -963,7 +984,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
             }
             *reinterpret_cast<int4 *>(trow + e4) = make_int4(val[0], val[1], val[2], val[3]);
         }
-        if (mn < (int)k && !dead) { // a symbol longer than the window: redo the round with the general parser
+        if (mn < (int)k && !dead && !(ABLATE & 14)) { // a symbol longer than the window: redo the round with the general parser
             if (vc_slow_round<RING>(s.row, s.rot, s.ce, &pos_s, k, trow, ROUND)) {
                 s.pos = pos_s;
                 s.load_window();
@@ -981,7 +1002,8 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
                 const int row = kRowsPerIt * it + lane / kRowLanes;
                 if ((row_mask >> row) & 1u) {
                     const int4 q = *reinterpret_cast<const int4 *>(tile + row * kTilePitch + (lane % kRowLanes) * 4);
-                    *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
+                    if (!(ABLATE & 1) || q.x == 0x7fffffff)
+                        *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
                 }
             }
             __syncwarp();
@@ -996,7 +1018,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
             else
                 bad |= s.pos > total * 32;
         }
-        if (bad)
+        if (bad && !(ABLATE & 14))
             p.flags[st] = 1u;
     }
 }

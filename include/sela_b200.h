@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELAB200_ABI_VERSION     1
+#define SELAB200_ABI_VERSION     2 /* 2: selab200_init_devices, selab200_device_count, selab200_rice_decode_flagged */
 #define SELAB200_FRAME_SAMPLES   2048 /* src/include/file/wav_file.hpp:12 */
 #define SELAB200_MAX_LPC_ORDER   100  /* src/include/lpc.hpp:7            */
 #define SELAB200_MAX_RICE_PARAM  20   /* src/include/rice.hpp:7           */

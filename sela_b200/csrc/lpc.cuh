@@ -30,6 +30,9 @@ struct AnalysisScratch {
     __device__ __forceinline__ double *t() { return ring + 104; }   // step-up scratch [0..99]
 };
 using LpcSmem = AnalysisScratch;
+// k[0..99] and the step-up row t[0..99] occupy doubles [0, 204) of the ring; from here to the end of ac[] the
+// scratch is free after warp_schur() (which reads ac[] into registers first): the encoder puts its CoefSmem there.
+constexpr size_t kCoefAlias = 208 * sizeof(double);
 
 __device__ __forceinline__ long long coef_at(const CoefSmem &cf, int j) // c[j], j >= 1
 {

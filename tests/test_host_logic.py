@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()                      # dlopen + getattr of every symbol
     for name in declared:
         assert hasattr(L, name)
-    assert L.selab200_abi_version() == 1
+    assert L.selab200_abi_version() == 2
 
 
 def test_descriptor_layout_matches_header_and_oracle():

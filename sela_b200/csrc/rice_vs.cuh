@@ -236,9 +236,10 @@ struct VsStream {
 // four lines per instruction instead of 32.  All calls are warp-convergent.
 struct VsCoopMeta { // per warp, in shared memory
     // rows that want a segment, each entry written by the row's owner and read by the eight lanes that copy
-    // it: x, y = source address of the segment; z = bytes of stream left from there (<= 0: zeros only);
-    // w = shared byte address of the segment's first word in the row's ring
-    uint4 list[32];
+    // it (and, a boundary later, reverse it): x, y = source address of the segment; z = bytes of stream left
+    // from there (<= 0: zeros only); w = shared byte address of the segment's first word in the row's ring.
+    // Two lists: the one being filled now and the one whose copies are landing.
+    uint4 list[2][32];
 };
 
 // add / subtract on the FMA pipe (IMAD.IADD): the parser is bound by the ALU pipe (shifts, logic, compares)
@@ -267,9 +268,9 @@ struct VsCoopStream {
     int total_bytes;          // bytes from gbase to the end of the stream (zeros behind)
     uint32_t pos, r0, r1, r2, wa;
     uint32_t fs;           // next segment to request
-    uint32_t ls;           // segments below ls have landed (and are reversed)
-    uint32_t seq, req_seq; // boundary counter; the boundary at which this lane's outstanding segment was requested
-    uint32_t ce;           // words below ce are readable
+    bool pending;          // the segment requested at the previous boundary is still on its way
+    int cur, n_prev;       // (warp-uniform) the list being filled; rows on the other one, whose copies are landing
+    uint32_t ce;           // words below ce are readable (landed and reversed)
     uint32_t seg_limit;    // no segment beyond this one is ever needed
 
     __device__ __forceinline__ uint32_t wb() const { return (pos >> 5) + 1; }
@@ -301,18 +302,19 @@ struct VsCoopStream {
         this->total_bytes = total_bytes;
         seg_limit = ((uint32_t)total_bytes >> 7) + 2;
     }
-    // Copy one segment for every lane with `want` (its `fs`); does not commit.
-    __device__ __forceinline__ void fill(bool want)
+    // Copy one segment for every lane with `want` (its `fs`) through list `which`; returns how many rows.  Does not commit.
+    __device__ __forceinline__ int fill(bool want, int which)
     {
         const int lane = lane_id();
         const uint32_t mask = __ballot_sync(kFull, want);
         if (mask == 0)
-            return;
+            return 0;
+        uint4 *list = meta->list[which];
         if (want) {
             const uint32_t off = fs * 128u;
             const int rem = total_bytes - (int)off;
             const unsigned long long src = gbase + (rem > 0 ? off : 0u);
-            meta->list[__popc(mask & ((1u << lane) - 1u))] =
+            list[__popc(mask & ((1u << lane) - 1u))] =
                 make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)rem, row | ((off + rot) & kMask));
         }
         __syncwarp();
@@ -321,40 +323,39 @@ struct VsCoopStream {
         for (int it = 0; it * 4 < n; it++) { // four rows per instruction, eight lanes x 16 bytes each
             const int idx = it * 4 + (lane >> 3);
             if (idx < n) {
-                const uint4 e = meta->list[idx];
+                const uint4 e = list[idx];
                 const int rem = (int)e.z - (int)piece;
                 const uint32_t sz = rem <= 0 ? 0u : rem < 16 ? (uint32_t)rem : 16u;
                 const unsigned long long src = (((unsigned long long)e.y << 32) | e.x) + (sz ? piece : 0u);
                 // the segment may wrap inside the row only at its end: it starts on a 128-byte boundary of the rotated row
                 const uint32_t dst = (e.w & ~kMask) | ((e.w + piece) & kMask);
                 if (!NOCOPY || sz == 77u)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
             }
         }
-        __syncwarp(); // the list is free again
+        return n;
     }
-    __device__ __forceinline__ void reverse_segment(uint32_t seg) const
+    // The segments of list `which` have landed: the lanes that copied them reverse them, one 16-byte piece each
+    // (all 32 lanes busy -- a lane reversing its own whole segment would leave the other 31 idle).  Convergent.
+    __device__ __forceinline__ void reverse_list(int which, int n) const
     {
-#pragma unroll
-        for (int v = 0; v < 8; v += 2) {
-            const uint32_t a = row | ((128 * seg + 16 * v + rot) & kMask), b = row | ((128 * seg + 16 * v + 16 + rot) & kMask);
-            uint32_t x0, y0, z0, w0, x1, y1, z1, w1;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(z0), "=r"(w0) : "r"(a));
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x1), "=r"(y1), "=r"(z1), "=r"(w1) : "r"(b));
-            x0 = __brev(x0), y0 = __brev(y0), z0 = __brev(z0), w0 = __brev(w0);
-            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x0), "r"(y0), "r"(z0), "r"(w0), "r"(a) : "memory");
-            x1 = __brev(x1), y1 = __brev(y1), z1 = __brev(z1), w1 = __brev(w1);
-            asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x1), "r"(y1), "r"(z1), "r"(w1), "r"(b) : "memory");
+        if (REVERSED) {
+            const int lane = lane_id();
+            const uint4 *list = meta->list[which];
+            const uint32_t piece = 16u * (lane & 7);
+            for (int it = 0; it * 4 < n; it++) {
+                const int idx = it * 4 + (lane >> 3);
+                if (idx < n) {
+                    const uint32_t w0 = list[idx].w;
+                    const uint32_t a = (w0 & ~kMask) | ((w0 + piece) & kMask);
+                    uint32_t x, y, z, w;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
+                    x = __brev(x), y = __brev(y), z = __brev(z), w = __brev(w);
+                    asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x), "r"(y), "r"(z), "r"(w), "r"(a) : "memory");
+                }
+            }
         }
-    }
-    __device__ __forceinline__ void retire(uint32_t upto)
-    {
-        while (ls < upto) {
-            if (REVERSED)
-                reverse_segment(ls);
-            ls++;
-        }
-        ce = kSeg * ls;
+        __syncwarp(); // reversed words visible to their owners; the list is free again
     }
     // (Re)start the lanes with `want` at bit p.  Convergent.
     __device__ __forceinline__ void prime(uint32_t p, bool want)
@@ -363,58 +364,57 @@ struct VsCoopStream {
         __syncwarp();
         if (want) {
             pos = p;
-            fs = ls = (wb() - 1) >> 5;
+            fs = (wb() - 1) >> 5;
         }
-        fill(want);
+        const int n0 = fill(want, 0);
         if (want)
             fs++;
-        fill(want);
+        const int n1 = fill(want, 1);
         if (want)
             fs++;
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
+        reverse_list(0, n0);
+        reverse_list(1, n1);
         if (want) {
-            retire(fs);
+            ce = kSeg * fs;
             load_window();
         }
-        seq = 0;
-        req_seq = 0;
+        cur = 0;
+        n_prev = 0;
+        pending = false;
     }
     // Top-up for the lanes with `want`.  Convergent.
-    // A segment is requested as soon as the parser has left the slot it goes to, but it is only waited for when
-    // a parser is about to run out of landed words -- typically two or three rounds later, so the copy has had
-    // that long to arrive (cp.async groups complete in order: waiting for "all but the last N groups" is waiting
-    // for a request N boundaries old).
     __device__ __forceinline__ void boundary(bool want)
     {
-        seq++;
         // segment fs goes where segment fs - 2 was: free once the parser (r0 = word wb - 1) has left it
         const uint32_t w = wb();
         const bool ready = want && kSeg * (fs - 1) <= w - 1 && fs <= seg_limit;
-        fill(ready);
-        if (ready) {
+        const int n_cur = fill(ready, cur);
+        cp_async_commit();
+        cp_async_wait<1>(); // what the previous boundary requested has landed ...
+        __syncwarp();       // ... for every lane of the warp
+        reverse_list(cur ^ 1, n_prev);
+        if (pending)
+            ce = kSeg * fs; // (fs still counts the segment requested at the previous boundary, not this one's)
+        pending = ready;
+        if (ready)
             fs++;
-            req_seq = seq;
-        }
-        cp_async_commit(); // one group per boundary, empty or not
-        // a round reads at most ROUND + 2 words past r1
-        const bool need = want && ls < fs && ce < w + ROUND + 3;
-        const uint32_t age = __reduce_min_sync(kFull, need ? seq - req_seq : 99u);
-        if (age != 99u) {
-            if (age == 0)
-                cp_async_wait<0>();
-            else if (age == 1)
-                cp_async_wait<1>();
-            else if (age == 2)
-                cp_async_wait<2>();
-            else
-                cp_async_wait<3>();
+        // A round reads at most ROUND + 2 words past r1.  A parser that entered its last landed segment late in
+        // a dense stretch needs the segment requested just now: wait for it (rare).
+        if (__any_sync(kFull, ready && ce < w + ROUND + 3)) {
+            cp_async_wait<0>();
             __syncwarp();
-            const uint32_t landed = age > 3 ? 3 : age;
-            if (want && ls < fs && seq - req_seq >= landed)
-                retire(fs);
+            reverse_list(cur, n_cur);
+            if (pending)
+                ce = kSeg * fs;
+            pending = false;
+            n_prev = 0;
+        } else {
+            n_prev = n_cur;
         }
+        cur ^= 1;
     }
 };
 

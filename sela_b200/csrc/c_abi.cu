@@ -475,7 +475,7 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
         if (int rc2 = set_smem(k_rice_decode_vc<16, 128>, smem))
             return rc2;
         k_rice_decode_vc<16, 128><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s);
-    } else if (geom >= 200 && geom < 216) { // ablations of the cooperative decoder: 200 + bit mask (8: no copy instruction)
+    } else if (geom >= 200 && geom < 232) { // ablations of the cooperative decoder: 200 + bit mask (8: no copy instruction)
         constexpr size_t smem = vc_smem_bytes<32>();
         switch (geom - 200) {
 #define SELAB200_ABL(m)                                                                    \
@@ -484,7 +484,7 @@ int launch_rice_residues(const DecodeParams &p, void *aux, cudaStream_t stream)
             return rc2;                                                                    \
         k_rice_decode_vc<16, 32, m><<<vs_blocks, 32 * kVsWarps, smem, stream>>>(q, log2s); \
         break;
-            SELAB200_ABL(1) SELAB200_ABL(2) SELAB200_ABL(3) SELAB200_ABL(4) SELAB200_ABL(5) SELAB200_ABL(6) SELAB200_ABL(7) SELAB200_ABL(8) SELAB200_ABL(12)
+            SELAB200_ABL(1) SELAB200_ABL(2) SELAB200_ABL(3) SELAB200_ABL(4) SELAB200_ABL(5) SELAB200_ABL(6) SELAB200_ABL(7) SELAB200_ABL(8) SELAB200_ABL(12) SELAB200_ABL(16)
 #undef SELAB200_ABL
         default: break;
         }

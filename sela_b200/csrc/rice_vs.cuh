@@ -263,6 +263,8 @@ struct VsCoopStream {
     static_assert(ROUND <= 16, "a round must not outrun one segment's slack");
     uint32_t row, rot;     // this lane's ring row (shared byte address, 256-aligned) and rotation
     uint32_t rows0;        // shared byte address of the warp's row 0
+    unsigned char *sbase;  // the kernel's dynamic shared memory as a pointer, and its shared byte address
+    uint32_t s0;
     VsCoopMeta *meta;
     unsigned long long gbase; // this lane's stream from its 16-byte aligned base
     int total_bytes;          // bytes from gbase to the end of the stream (zeros behind)
@@ -291,9 +293,11 @@ struct VsCoopStream {
         wa = fma_add(wa, 4);
         r2 = lds_u32(row | (wa & kMask));
     }
-    __device__ __forceinline__ void setup(uint32_t rows0_, VsCoopMeta *m, const uint4 *gvec, int total_bytes)
+    __device__ __forceinline__ void setup(unsigned char *smem, uint32_t rows0_, VsCoopMeta *m, const uint4 *gvec, int total_bytes)
     {
         const int lane = lane_id();
+        sbase = smem;
+        s0 = (uint32_t)__cvta_generic_to_shared(smem);
         rows0 = rows0_;
         row = rows0_ + (uint32_t)lane * (kRing * 4);
         rot = (16u * lane) & kMask;
@@ -348,10 +352,11 @@ struct VsCoopStream {
                 if (idx < n) {
                     const uint32_t w0 = list[idx].w;
                     const uint32_t a = (w0 & ~kMask) | ((w0 + piece) & kMask);
-                    uint32_t x, y, z, w;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
-                    x = __brev(x), y = __brev(y), z = __brev(z), w = __brev(w);
-                    asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(x), "r"(y), "r"(z), "r"(w), "r"(a) : "memory");
+                    // (plain loads through the shared array: behind an inline-asm load ptxas lowers BREV to three instructions)
+                    uint4 *q = reinterpret_cast<uint4 *>(sbase + (a - s0));
+                    uint4 v = *q;
+                    v.x = __brev(v.x), v.y = __brev(v.y), v.z = __brev(v.z), v.w = __brev(v.w);
+                    *q = v;
                 }
             }
         }
@@ -945,7 +950,7 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
     const uint32_t skip = (uint32_t)(addr >> 2) & 3u;
     const uint32_t total = ok && d.res_words ? (uint32_t)d.res_words + skip : 0u;
     Stream s;
-    s.setup(smem0 + pad + (uint32_t)(warp * 32) * (RING * 4), meta, reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15), (int)(total * 4));
+    s.setup(vc_smem, smem0 + pad + (uint32_t)(warp * 32) * (RING * 4), meta, reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15), (int)(total * 4));
     const uint32_t k = ok ? d.res_rice_param : 0u, kp1 = k + 1, kk = 32 - k, kpow = 1u << k;
     const uint32_t row_mask = __ballot_sync(kFull, store_row);
 
@@ -1002,8 +1007,12 @@ __global__ void __launch_bounds__(32 * kVsWarps) k_rice_decode_vc(RiceVsParams p
                 const int row = kRowsPerIt * it + lane / kRowLanes;
                 if ((row_mask >> row) & 1u) {
                     const int4 q = *reinterpret_cast<const int4 *>(tile + row * kTilePitch + (lane % kRowLanes) * 4);
-                    if (!(ABLATE & 1) || q.x == 0x7fffffff)
-                        *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
+                    if (!(ABLATE & 1) || q.x == 0x7fffffff) {
+                        if (ABLATE & 16)
+                            __stcs(reinterpret_cast<int4 *>(dst + (size_t)row * part), q);
+                        else
+                            *reinterpret_cast<int4 *>(dst + (size_t)row * part) = q;
+                    }
                 }
             }
             __syncwarp();

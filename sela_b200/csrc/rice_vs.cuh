@@ -98,16 +98,17 @@ struct VsRing {
         const uint32_t off = 16 * fv;
         const uint32_t dst = row | ((off + rot) & kMask);
         if ((int)(off + 16) <= total_bytes) { // the common case: a whole vector of the stream
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + off) : "memory");
         } else { // the ragged end, and zeros behind it
             const int rem = total_bytes - (int)off;
             const uint32_t sz = rem <= 0 ? 0u : (uint32_t)rem;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + (sz ? off : 0u)), "r"(sz) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(reinterpret_cast<const char *>(gvec) + (sz ? off : 0u)), "r"(sz) : "memory");
         }
     }
     // The value parser wants the stream MSB first (a leading-zero count finds the terminator, the payload
-    // reads as a number); BREV costs three issue slots on sm_100a, so the words are reversed once, in place,
-    // when their vector has landed -- not once per symbol.
+    // reads as a number); the words are reversed once, in place, when their vector has landed -- one BREV per
+    // word instead of one per symbol.  (Behind an inline-asm shared load ptxas lowers BREV to three instructions;
+    // VsCoopStream::reverse_list uses plain loads for that reason.)
     __device__ __forceinline__ void reverse(uint32_t v) const
     {
         const uint32_t a = row | ((16 * v + rot) & kMask);
@@ -233,7 +234,10 @@ struct VsStream {
 // with the top-ups removed runs 2.3x faster).  Here the 32 rings of a warp are topped up COOPERATIVELY in
 // 128-byte segments: a ring is two segments of 32 words; a lane whose parser has left a segment puts its
 // row on a list, and eight lanes copy one row's next segment (8 x 16 bytes = one whole line) -- four rows,
-// four lines per instruction instead of 32.  All calls are warp-convergent.
+// four lines per instruction instead of 32 -- and, when it has landed, reverse it the same way.  The copies
+// bypass L1 (cp.async.cg): every line is fetched exactly once, and letting those lines allocate in the 16 KB
+// of L1 the kernel leaves was the second wall (1.43 -> 1.19 ms at 413 k streams).  All calls are
+// warp-convergent.
 struct VsCoopMeta { // per warp, in shared memory
     // rows that want a segment, each entry written by the row's owner and read by the eight lanes that copy
     // it (and, a boundary later, reverse it): x, y = source address of the segment; z = bytes of stream left

@@ -179,6 +179,24 @@ struct ChunkPlan {
     uint32_t max_frames = 0;     // largest chunk (sizes the per-lane workspace)
     uint32_t chunks() const { return (uint32_t)start.size() - 1; }
 };
+// decode-side knobs for measurements: SELAB200_DEC_PARTS (target chunk count), SELAB200_DEC_TAPER=1
+uint32_t dec_parts()
+{
+    if (const char *e = std::getenv("SELAB200_DEC_PARTS")) {
+        const long v = std::atol(e);
+        if (v >= 1 && v <= 64)
+            return (uint32_t)v;
+    }
+    return 8;
+}
+bool dec_taper()
+{
+    // round 1 kept equal chunks for decode (small chunks starved the lane-per-stream Rice kernel); with streams cut
+    // into parts for small batches (rice_vs.cuh) the shrinking first and last chunks pay here too: decode call 3.80 -> 3.67 ms
+    const char *e = std::getenv("SELAB200_DEC_TAPER");
+    return !(e && e[0] == '0');
+}
+
 ChunkPlan plan_chunks(uint32_t n_frames, uint32_t parts, bool allow_taper)
 {
     ChunkPlan p;
@@ -960,7 +978,7 @@ static int decode_host(const selab200_subframe_desc *descs, uint32_t n_frames, u
     // Every chunk gets its own compute lane (up to kLanes): the Rice kernel is one lane per stream
     // and latency-bound (about 0.4 ms however small the chunk), so the chunks' Rice kernels must
     // overlap each other and the synthesis kernels of earlier chunks rather than queue up.
-    const ChunkPlan plan = plan_chunks(n_frames, 8, false);
+    const ChunkPlan plan = plan_chunks(n_frames, dec_parts(), dec_taper());
     const uint32_t n_chunks = plan.chunks();
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;
@@ -1431,7 +1449,7 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
     PipelineDrain drain;
-    const ChunkPlan plan = plan_chunks(n_frames, 8, false);
+    const ChunkPlan plan = plan_chunks(n_frames, dec_parts(), dec_taper());
     const uint32_t n_chunks = plan.chunks();
     const size_t n_sub = (size_t)n_frames * channels;
     const size_t frame_bytes = (size_t)channels * kFrame * 2;

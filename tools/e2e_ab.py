@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 var, vals, reps = sys.argv[1], sys.argv[2:4], int(sys.argv[4]) if len(sys.argv) > 4 else 2
 for rep in range(reps):
     for v in vals:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "60", "--warmup", "3", "--no-cpu"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "40", "--warmup", "3", "--no-cpu", "--no-sharded"],
                            env=dict(os.environ, **{var: v}), capture_output=True, text=True, timeout=900)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])

@@ -93,6 +93,7 @@ struct Context {
 constexpr int kMaxDevices = 16;
 Context g_slots[kMaxDevices];
 int g_n_ctx = 0;
+Context *g_last_rice_ctx = nullptr; // the context selab200_rice_decode_frames_device last ran on (flag count query)
 thread_local Context *tl_ctx = &g_slots[0];
 #define g (*tl_ctx)
 
@@ -676,6 +677,8 @@ static void shutdown_slot()
     g.ready = false;
     g.device = -1;
     g.last_rice_n_sub = 0;
+    if (g_last_rice_ctx == tl_ctx)
+        g_last_rice_ctx = nullptr;
 }
 
 static void shutdown_all()
@@ -848,6 +851,7 @@ int selab200_rice_decode_frames_device(const selab200_subframe_desc *d_descs, ui
         return rc;
     g.last_rice_n_sub = (size_t)n_frames * channels;
     g.last_rice_stream = (cudaStream_t)stream;
+    g_last_rice_ctx = tl_ctx;
     return launch_rice_residues(p, g.aux.ptr, (cudaStream_t)stream);
 }
 
@@ -859,6 +863,10 @@ int selab200_rice_decode_flagged(uint32_t *n_flagged)
     if (!n_flagged)
         return fail(SELAB200_ERR_ARGUMENT, "null pointer");
     *n_flagged = 0;
+    if (g_last_rice_ctx && g_last_rice_ctx->ready) { // the device the last call ran on, which need not be the primary
+        tl_ctx = g_last_rice_ctx;
+        CUDA_TRY(cudaSetDevice(g.device));
+    }
     const size_t n = g.last_rice_n_sub;
     if (n == 0 || g.aux.bytes < n * 64)
         return 0;
@@ -1332,6 +1340,7 @@ void selab200_container_close(selab200_container *h)
     if (!h)
         return;
     std::lock_guard<std::mutex> lock(g_mutex);
+    tl_ctx = &g_slots[0]; // container handles belong to the primary device
     if (g.ready)
         cudaSetDevice(g.device); // the caller may be on a thread that never selected the device
     if (g.s_h2d)

@@ -1443,6 +1443,92 @@ int selab200_container_open(const uint8_t *container, size_t n_bytes, selab200_c
     return 0;
 }
 
+} // extern "C"
+
+// Frames [F0, F0 + NF) of an open container on the device of the current context.  The primary device holds the
+// whole byte image (uploaded by selab200_container_open, in pieces with events); any other device uploads just
+// the bytes of its block.  The word arena keeps the descriptors' file-order offsets: it is addressed through a
+// pointer shifted back by the block's first word, so nothing is re-based.
+static int container_decode_block(selab200_container *h, uint32_t F0, uint32_t NF, int16_t *pcm_out, bool primary)
+{
+    if (NF == 0)
+        return 0;
+    const uint32_t channels = h->info.channels;
+    const selab200_subframe_desc *hd = h->buf.h_descs;
+    PipelineDrain drain;
+    const ChunkPlan plan = plan_chunks(NF, dec_parts(), dec_taper());
+    const uint32_t n_chunks = plan.chunks();
+    const size_t n_sub = (size_t)NF * channels;
+    const size_t frame_bytes = (size_t)channels * kFrame * 2;
+    const size_t ws_bytes = selab200_decode_workspace_bytes(plan.max_frames, channels);
+    const size_t n_words = (size_t)h->info.n_words;
+    const unsigned long long w_lo = hd[(size_t)F0 * channels].refl_offset;
+    const selab200_subframe_desc &tail = hd[(size_t)(F0 + NF) * channels - 1];
+    const unsigned long long w_hi = tail.res_offset + tail.res_words;
+    const unsigned long long b_lo = container_frame_byte(F0, channels, w_lo);
+    const unsigned long long b_hi = container_frame_byte(F0 + NF, channels, w_hi);
+    if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
+    if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
+    if (int rc = g.words.ensure((size_t)(w_hi - w_lo) * 4 + 96)) return rc;
+    for (int i = 0; i < kLanes && (uint32_t)i < n_chunks; i++)
+        if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
+    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
+    int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
+    selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
+    // 16 bytes of slack in front (the Rice decoder reads whole 16-byte vectors), the 16-byte phase of file order kept
+    uint32_t *d_arena = reinterpret_cast<uint32_t *>(static_cast<char *>(g.words.ptr) + 16 + ((w_lo * 4) & 15)) - w_lo;
+    const uint8_t *d_bytes = static_cast<const uint8_t *>(h->buf.d_bytes);
+    if (!primary) {
+        const unsigned long long b0 = b_lo & ~3ull; // the unpack kernel reads aligned 32-bit words of the byte image
+        const size_t end = std::min<size_t>(h->n_bytes, (size_t)b_hi + 4);
+        if (int rc = g.aux.ensure(end - (size_t)b0 + 64)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(g.aux.ptr, h->bytes + b0, end - (size_t)b0, cudaMemcpyHostToDevice, g.s_h2d));
+        CUDA_TRY(cudaEventRecord(g.ev_h2d[0], g.s_h2d));
+        d_bytes = static_cast<const uint8_t *>(g.aux.ptr) - b0;
+    }
+
+    CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
+    CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
+    for (int i = 1; i < kLanes; i++)
+        CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0; // within the block
+        const selab200_subframe_desc *dc = hd + (size_t)(F0 + f0) * channels;
+        const size_t chunk_sub = (size_t)nf * channels;
+        cudaStream_t cs = g.s_compute[c % kLanes];
+        DeviceBuffer &ws = g.lane_work[c % kLanes];
+        // descriptors go up on the chunk's own lane: s_h2d is still busy with the container bytes
+        CUDA_TRY(cudaMemcpyAsync(d_descs + (size_t)f0 * channels, dc, chunk_sub * sizeof(*dc), cudaMemcpyHostToDevice, cs));
+        if (primary) {
+            // the container bytes this chunk reads end with its last subframe (+3 bytes of slack)
+            const selab200_subframe_desc &last = dc[chunk_sub - 1];
+            const unsigned long long end_byte =
+                container_frame_byte(F0 + f0 + nf, channels, last.res_offset + last.res_words) + 3;
+            int piece = (int)(end_byte / h->piece_bytes);
+            if (piece >= h->n_pieces)
+                piece = h->n_pieces - 1;
+            CUDA_TRY(cudaStreamWaitEvent(cs, h->buf.ev_piece[piece], 0));
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(cs, g.ev_h2d[0], 0));
+        }
+        k_container_unpack<<<(unsigned)((chunk_sub + 7) / 8), 256, 0, cs>>>(d_bytes, d_descs + (size_t)f0 * channels,
+                                                                           (uint32_t)chunk_sub, channels,
+                                                                           (unsigned long long)(F0 + f0) * channels, d_arena);
+        if (int rc = launch_check("k_container_unpack"))
+            return rc;
+        if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_arena, n_words,
+                                   d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))
+            return rc;
+        CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
+        CUDA_TRY(cudaStreamWaitEvent(g.s_d2h, g.ev_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(pcm_out + (size_t)(F0 + f0) * channels * kFrame, d_pcm + (size_t)f0 * channels * kFrame,
+                                 nf * frame_bytes, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    return read_status(g.s_d2h, d_status);
+}
+
+extern "C" {
+
 int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -1457,58 +1543,11 @@ int selab200_container_decode(selab200_container *h, int16_t *pcm_out)
         return fail(SELAB200_ERR_ARGUMENT, "null pointer");
     if (channels == 0 || channels > SELAB200_MAX_CHANNELS)
         return fail(SELAB200_ERR_ARGUMENT, "channels must be in [1, %d]", SELAB200_MAX_CHANNELS);
-    PipelineDrain drain;
-    const ChunkPlan plan = plan_chunks(n_frames, dec_parts(), dec_taper());
-    const uint32_t n_chunks = plan.chunks();
-    const size_t n_sub = (size_t)n_frames * channels;
-    const size_t frame_bytes = (size_t)channels * kFrame * 2;
-    const size_t ws_bytes = selab200_decode_workspace_bytes(plan.max_frames, channels);
-    const size_t n_words = (size_t)h->info.n_words;
-    if (int rc = g.in.ensure(n_sub * kFrame * 2)) return rc;
-    if (int rc = g.descs.ensure(n_sub * sizeof(selab200_subframe_desc))) return rc;
-    if (int rc = g.words.ensure(n_words * 4 + 64)) return rc;
-    for (int i = 0; i < kLanes && (uint32_t)i < n_chunks; i++)
-        if (int rc = g.lane_work[i].ensure(ws_bytes)) return rc;
-    int32_t *d_status = static_cast<int32_t *>(g.small.ptr);
-    int16_t *d_pcm = static_cast<int16_t *>(g.in.ptr);
-    selab200_subframe_desc *d_descs = static_cast<selab200_subframe_desc *>(g.descs.ptr);
-    uint32_t *d_arena = static_cast<uint32_t *>(g.words.ptr);
-    const uint8_t *d_bytes = static_cast<const uint8_t *>(h->buf.d_bytes);
-
-    CUDA_TRY(cudaMemsetAsync(g.small.ptr, 0, 16, g.s_compute[0]));
-    CUDA_TRY(cudaEventRecord(g.ev_reset, g.s_compute[0]));
-    for (int i = 1; i < kLanes; i++)
-        CUDA_TRY(cudaStreamWaitEvent(g.s_compute[i], g.ev_reset, 0));
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = plan.start[c], nf = plan.start[c + 1] - f0;
-        const selab200_subframe_desc *dc = h->buf.h_descs + (size_t)f0 * channels;
-        const size_t chunk_sub = (size_t)nf * channels;
-        cudaStream_t cs = g.s_compute[c % kLanes];
-        DeviceBuffer &ws = g.lane_work[c % kLanes];
-        // descriptors go up on the chunk's own lane: s_h2d is still busy with the container pieces
-        CUDA_TRY(cudaMemcpyAsync(d_descs + (size_t)f0 * channels, dc, chunk_sub * sizeof(*dc), cudaMemcpyHostToDevice, cs));
-        // the container bytes this chunk reads end with its last subframe (+3 bytes of slack)
-        const selab200_subframe_desc &last = dc[chunk_sub - 1];
-        const unsigned long long end_byte =
-            container_frame_byte(f0 + nf, channels, last.res_offset + last.res_words) + 3;
-        int piece = (int)(end_byte / h->piece_bytes);
-        if (piece >= h->n_pieces)
-            piece = h->n_pieces - 1;
-        CUDA_TRY(cudaStreamWaitEvent(cs, h->buf.ev_piece[piece], 0));
-        k_container_unpack<<<(unsigned)((chunk_sub + 7) / 8), 256, 0, cs>>>(d_bytes, d_descs + (size_t)f0 * channels,
-                                                                           (uint32_t)chunk_sub, channels,
-                                                                           (unsigned long long)f0 * channels, d_arena);
-        if (int rc = launch_check("k_container_unpack"))
-            return rc;
-        if (int rc = decode_device(d_descs + (size_t)f0 * channels, nf, channels, d_arena, n_words,
-                                   d_pcm + (size_t)f0 * channels * kFrame, d_status, ws.ptr, ws.bytes, cs, false))
-            return rc;
-        CUDA_TRY(cudaEventRecord(g.ev_done[c], cs));
-        CUDA_TRY(cudaStreamWaitEvent(g.s_d2h, g.ev_done[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(pcm_out + (size_t)f0 * channels * kFrame, d_pcm + (size_t)f0 * channels * kFrame,
-                                 nf * frame_bytes, cudaMemcpyDeviceToHost, g.s_d2h));
-    }
-    return read_status(g.s_d2h, d_status);
+    if (!use_all_devices(n_frames))
+        return container_decode_block(h, 0, n_frames, pcm_out, true);
+    // one block of frames per device; the primary (which holds the whole image) takes the first
+    std::vector<DevicePart> parts = device_parts(n_frames);
+    return run_on_devices(parts, [&](DevicePart &p) { return container_decode_block(h, p.f0, p.nf, pcm_out, tl_ctx == &g_slots[0]); });
 }
 
 int selab200_selftest(uint32_t *mismatches)

@@ -77,11 +77,11 @@ typedef struct selab200_subframe_desc {
 int  selab200_init(int device);
 /* Several devices of one box (selagpu_init(device_count, device_ids)): every device gets a
  * context of its own (streams, events, pools).  The host-buffer batch calls (selab200_encode_frames,
- * selab200_decode_frames, selab200_encode_container) then cut the frames into one contiguous block per device
+ * selab200_decode_frames, selab200_encode_container, selab200_container_decode) then cut the frames into one contiguous block per device
  * -- n/D frames each, the last device takes the rest, the way sela::Encoder::processFrames cuts them for its
  * threads (src/sela/encoder.cpp:58-73) -- and run the blocks concurrently, reading and writing disjoint ranges
  * of the caller's buffers; results are byte-identical to a single device's.  devices[0] is the primary: it
- * serves the stage-level and container-decode calls.  The *_device forms run on whichever initialised device
+ * serves the stage-level calls and holds the byte image of an open container.  The *_device forms run on whichever initialised device
  * owns the buffers they are given. */
 int  selab200_init_devices(int count, const int *devices);
 int  selab200_device_count(void);

@@ -1,8 +1,11 @@
 """Host-buffer timings of the C ABI with one device and with several (selab200_init_devices):
 the same pinned buffers, the same calls.  Usage: python tools/multi_device_e2e.py [n_devices] [minutes]"""
 import json
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 import numpy as np
 

@@ -355,11 +355,16 @@ int encode_device(const int16_t *d_pcm, uint32_t n_frames, uint32_t channels, se
     }
     if (int rc = launch_check("k_encode_units"))
         return rc;
+    const unsigned scan_ctas = (unsigned)((n_sub + kScanTile - 1) / kScanTile);
+    k_encode_sizes<<<scan_ctas, kScanTile, 0, stream>>>(p);
+    if (int rc = launch_check("k_encode_sizes"))
+        return rc;
     if (before_scan)
         CUDA_TRY(cudaStreamWaitEvent(stream, before_scan, 0));
-    k_encode_scan<<<1, 1024, 0, stream>>>(p);
+    k_encode_scan<<<scan_ctas, kScanTile, 0, stream>>>(p);
     if (int rc = launch_check("k_encode_scan"))
         return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_used, p.residues, 8, cudaMemcpyDeviceToDevice, stream)); // the new fill level (see k_encode_scan)
     // The fill level this chunk leaves behind must be captured BEFORE the next chunk's scan (on the
     // other compute lane) may overwrite *d_used: copy it out now and only then release the event.
     if (h_fill_after)
@@ -561,7 +566,11 @@ int decode_device(const selab200_subframe_desc *d_descs, uint32_t n_frames, uint
     void *rice_aux = reinterpret_cast<char *>(p.order_index) + align256((n_sub + 16) * 4);
     const size_t n_slots = (n_sub + 12 + 3) / 4 * 4; // every class segment starts on a warp boundary
     CUDA_TRY(cudaMemsetAsync(p.order_index, 0xff, n_slots * 4, stream));
-    k_decode_classify<<<1, 1024, 0, stream>>>(p);
+    const unsigned class_ctas = (unsigned)((n_sub + kScanTile - 1) / kScanTile);
+    k_decode_class_counts<<<class_ctas, kScanTile, 0, stream>>>(p, static_cast<ClassCounts *>(rice_aux));
+    if (int rc = launch_check("k_decode_class_counts"))
+        return rc;
+    k_decode_classify<<<class_ctas, kScanTile, 0, stream>>>(p, static_cast<const ClassCounts *>(rice_aux));
     if (int rc = launch_check("k_decode_classify"))
         return rc;
     if (int rc = launch_rice_decode(p, 0, stream))

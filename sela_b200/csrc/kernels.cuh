@@ -33,7 +33,7 @@ namespace selab200 {
 constexpr uint32_t kSlotWords = 1600;     // per-unit scratch slot (refl words first, then residue words)
 constexpr uint32_t kSlotReflWords = 32;   // 100 coefficients * (8 + 1) bits <= 29 words
 
-struct UnitRecord {                       // 32 bytes
+struct __align__(16) UnitRecord {         // 32 bytes
     uint32_t order;
     uint32_t refl_k, refl_words;
     uint32_t res_k, res_words;
@@ -169,6 +169,22 @@ constexpr size_t encode_smem_bytes()
     return (size_t)(kHistoryPad + kFrame) * 2 + (STEREO ? (kHistoryPad + kFrame) / 8 : 0) + sizeof(AnalysisScratch);
 }
 
+// Warp copy of n words, eight loads in flight per lane before the first store (a load-store-load-store loop leaves
+// ONE: the in-order issue stops at every store until its load has landed).  The source is read once and dead after.
+__device__ __forceinline__ void warp_copy_words(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t n, int lane)
+{
+    for (uint32_t w = lane; w < n; w += 256) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            v[j] = w + 32 * j < n ? __ldcs(src + w + 32 * j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (w + 32 * j < n)
+                dst[w + 32 * j] = v[j];
+    }
+}
+
 // Which unit is emitted for output subframe (frame, channel), and as what.
 struct Emit {
     uint32_t unit, type, parent;
@@ -198,79 +214,130 @@ __device__ __forceinline__ Emit choose_unit(const UnitRecord *units, uint32_t ch
     return e;
 }
 
-__global__ void __launch_bounds__(1024) k_encode_scan(EncodeParams p)
+// The unit emitted for subframe `sub` together with its record (for a stereo side channel the winner is one of the
+// two records the decision reads anyway).
+__device__ __forceinline__ Emit choose_record(const UnitRecord *units, uint32_t channels, uint32_t sub, UnitRecord &u)
 {
-    // One CTA walks the emitted subframes in file order, 1024 at a time: coalesced unit-record
-    // loads, a shuffle-based block scan of the sizes, descriptors out; the running fill level is
-    // carried from tile to tile (and, through *words_used, from chunk to chunk of a pipelined call).
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry;
-    const uint32_t n_sub = p.n_frames * p.channels;
+    Emit e;
+    if (channels != 2 || (sub & 1) == 0) {
+        e.unit = channels != 2 ? sub : 3 * (sub >> 1);
+        e.type = 0;
+        e.parent = channels != 2 ? sub % channels : 0;
+        u = units[e.unit];
+        return e;
+    }
+    const uint32_t frame = sub >> 1;
+    const UnitRecord a = units[3 * frame + 1], d = units[3 * frame + 2];
+    const bool diff_wins = (unsigned long long)d.refl_words + d.res_words <
+                           (unsigned long long)a.refl_words + a.res_words; // strictly smaller
+    e.unit = 3 * frame + (diff_wins ? 2 : 1);
+    e.type = diff_wins ? 1 : 0;
+    e.parent = diff_wins ? 0 : 1;
+    u = diff_wins ? d : a;
+    return e;
+}
+
+// Block-wide inclusive scan of one 64-bit value per thread (1024 threads); warp_tot[31] is the block total afterwards.
+__device__ __forceinline__ unsigned long long block_scan_inclusive_u64(unsigned long long v, unsigned long long *warp_tot)
+{
     const int lane = lane_id(), warp = warp_id();
-    if (threadIdx.x == 0)
-        carry = *p.words_used;
-    bool bad = false;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o)
+            v += t;
+    }
+    if (lane == 31)
+        warp_tot[warp] = v;
     __syncthreads();
-    for (uint32_t tile = 0; tile < n_sub; tile += 1024) {
-        const uint32_t sub = tile + threadIdx.x;
-        Emit e;
-        UnitRecord u;
-        unsigned long long size = 0;
-        if (sub < n_sub) {
-            e = choose_unit(p.units, p.channels, sub);
-            u = p.units[e.unit];
-            size = (unsigned long long)u.refl_words + u.res_words;
-            bad |= u.flags != 0 || u.refl_words > 0xffffu || u.res_words > 0xffffu;
-        }
-        unsigned long long incl = size;
+    if (warp == 0) {
+        unsigned long long w = warp_tot[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(kFull, incl, o);
+            const unsigned long long t = __shfl_up_sync(kFull, w, o);
             if (lane >= o)
-                incl += t;
+                w += t;
         }
-        if (lane == 31)
-            warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(kFull, w, o);
-                if (lane >= o)
-                    w += t;
-            }
-            warp_tot[lane] = w; // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned long long base = carry + (warp ? warp_tot[warp - 1] : 0);
-        if (sub < n_sub) {
-            const unsigned long long off = base + incl - size;
-            selab200_subframe_desc v;
-            v.channel = (uint8_t)(sub % p.channels);
-            v.subframe_type = (uint8_t)e.type;
-            v.parent_channel = (uint8_t)e.parent;
-            v.refl_rice_param = (uint8_t)u.refl_k;
-            v.refl_words = (uint16_t)u.refl_words;
-            v.lpc_order = (uint8_t)u.order;
-            v.res_rice_param = (uint8_t)u.res_k;
-            v.res_words = (uint16_t)u.res_words;
-            v.samples = (uint16_t)kFrame;
-            v.reserved = 0;
-            v.refl_offset = off;
-            v.res_offset = off + u.refl_words;
-            p.descs[sub] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-            carry += warp_tot[31];
-        __syncthreads();
+        warp_tot[lane] = w; // inclusive over warps
+    }
+    __syncthreads();
+    return v + (warp ? warp_tot[warp - 1] : 0ull);
+}
+
+// The scan of the emitted sizes (stereo decision, exclusive prefix sum in file order, descriptors, fill level) in two
+// launches of 1024 subframes per CTA, coalesced record loads in both:
+//   k_encode_sizes   CTA b: total words of its 1024 subframes -> tmp[1 + b]           (independent of earlier chunks)
+//   k_encode_scan    CTA b: fill level so far (*words_used, left by the previous chunk of a pipelined call) + the
+//                    totals of the CTAs before it + a block scan -> descriptors; the last CTA leaves the new fill level
+//                    in tmp[0] (the host side copies it to *words_used: other CTAs may still be reading the old one).
+// tmp is the head of the residue workspace, dead once k_encode_units has finished.
+constexpr uint32_t kScanTile = 1024;
+
+__global__ void __launch_bounds__(kScanTile) k_encode_sizes(EncodeParams p)
+{
+    __shared__ unsigned long long warp_tot[32];
+    const uint32_t n_sub = p.n_frames * p.channels;
+    const uint32_t sub = blockIdx.x * kScanTile + threadIdx.x;
+    unsigned long long size = 0;
+    if (sub < n_sub) {
+        UnitRecord u;
+        choose_record(p.units, p.channels, sub, u);
+        size = (unsigned long long)u.refl_words + u.res_words;
+    }
+    block_scan_inclusive_u64(size, warp_tot);
+    if (threadIdx.x == 0)
+        reinterpret_cast<unsigned long long *>(p.residues)[1 + blockIdx.x] = warp_tot[31];
+}
+
+__global__ void __launch_bounds__(kScanTile) k_encode_scan(EncodeParams p)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long before;
+    unsigned long long *tmp = reinterpret_cast<unsigned long long *>(p.residues);
+    const uint32_t n_sub = p.n_frames * p.channels;
+    const uint32_t sub = blockIdx.x * kScanTile + threadIdx.x;
+    const int lane = lane_id(), warp = warp_id();
+    if (warp == 0) { // words in front of this CTA
+        unsigned long long s = lane == 0 ? *p.words_used : 0ull;
+        for (uint32_t b = lane; b < blockIdx.x; b += 32)
+            s += tmp[1 + b];
+        s = warp_sum_u64(s);
+        if (lane == 0)
+            before = s;
+    }
+    Emit e;
+    UnitRecord u;
+    unsigned long long size = 0;
+    bool bad = false;
+    if (sub < n_sub) {
+        e = choose_record(p.units, p.channels, sub, u);
+        size = (unsigned long long)u.refl_words + u.res_words;
+        bad = u.flags != 0 || u.refl_words > 0xffffu || u.res_words > 0xffffu;
+    }
+    const unsigned long long incl = block_scan_inclusive_u64(size, warp_tot); // its barriers also publish `before`
+    if (sub < n_sub) {
+        const unsigned long long off = before + incl - size;
+        selab200_subframe_desc v;
+        v.channel = (uint8_t)(sub % p.channels);
+        v.subframe_type = (uint8_t)e.type;
+        v.parent_channel = (uint8_t)e.parent;
+        v.refl_rice_param = (uint8_t)u.refl_k;
+        v.refl_words = (uint16_t)u.refl_words;
+        v.lpc_order = (uint8_t)u.order;
+        v.res_rice_param = (uint8_t)u.res_k;
+        v.res_words = (uint16_t)u.res_words;
+        v.samples = (uint16_t)kFrame;
+        v.reserved = 0;
+        v.refl_offset = off;
+        v.res_offset = off + u.refl_words;
+        p.descs[sub] = v;
     }
     if (bad)
         raise_status(p.status, SELAB200_ERR_RANGE); // a stream the uint16 word counts cannot describe
-    if (threadIdx.x == 0) {
-        *p.words_used = carry;
-        if (carry > p.capacity)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const unsigned long long fill = before + warp_tot[31];
+        tmp[0] = fill;
+        if (fill > p.capacity)
             raise_status(p.status, SELAB200_ERR_CAPACITY);
     }
 }
@@ -286,13 +353,8 @@ __global__ void __launch_bounds__(256) k_encode_gather(EncodeParams p)
     const Emit e = choose_unit(p.units, p.channels, sub);
     const selab200_subframe_desc d = p.descs[sub];
     const uint32_t *slot = p.slots + (size_t)e.unit * kSlotWords;
-    uint32_t *dst = p.words + d.refl_offset;
-    for (uint32_t w = lane; w < d.refl_words; w += 32)
-        dst[w] = slot[w];
-    dst = p.words + d.res_offset;
-    slot += kSlotReflWords;
-    for (uint32_t w = lane; w < d.res_words; w += 32)
-        dst[w] = slot[w];
+    warp_copy_words(p.words + d.refl_offset, slot, d.refl_words, lane);
+    warp_copy_words(p.words + d.res_offset, slot + kSlotReflWords, d.res_words, lane);
 }
 
 // --------------------------------------------------------------- container --
@@ -326,12 +388,22 @@ __device__ __forceinline__ void put_words_at_byte(uint8_t *out, unsigned long lo
     const uint32_t s = (uint32_t)(D & 3);
     uint32_t *dst = reinterpret_cast<uint32_t *>(out + (D - s));
     if (s == 0) {
-        for (uint32_t t = lane; t < n; t += 32)
-            dst[t] = src[t];
+        warp_copy_words(dst, src, n, lane);
         return;
     }
-    for (uint32_t t = 1 + lane; t < n; t += 32) // aligned word t = high bytes of src[t-1], low bytes of src[t]
-        dst[t] = __funnelshift_l(src[t - 1], src[t], 8 * s);
+    // aligned word t = high bytes of src[t-1], low bytes of src[t]; four words per lane loaded before the first store
+    for (uint32_t t0 = 1 + lane; t0 < n; t0 += 128) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t t = t0 + 32 * j;
+            v[j] = t < n ? __funnelshift_l(src[t - 1], src[t], 8 * s) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (t0 + 32 * j < n)
+                dst[t0 + 32 * j] = v[j];
+    }
     if (lane < (int)(4 - s))
         out[D + lane] = (uint8_t)(src[0] >> (8 * lane));
     else if (lane >= 4 && lane < (int)(4 + s))
@@ -345,8 +417,18 @@ __device__ __forceinline__ void get_words_at_byte(const uint8_t *in, unsigned lo
     const int lane = lane_id();
     const uint32_t s = (uint32_t)(D & 3);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (D - s));
-    for (uint32_t t = lane; t < n; t += 32)
-        dst[t] = s ? __funnelshift_r(src[t], src[t + 1], 8 * s) : src[t];
+    for (uint32_t t0 = lane; t0 < n; t0 += 128) { // four words per lane loaded before the first store
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t t = t0 + 32 * j;
+            v[j] = t < n ? (s ? __funnelshift_r(src[t], src[t + 1], 8 * s) : src[t]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (t0 + 32 * j < n)
+                dst[t0 + 32 * j] = v[j];
+    }
 }
 
 // Encoder output straight into the container: k_encode_gather with byte-packed destinations
@@ -580,81 +662,96 @@ __device__ __forceinline__ int order_class(int order) { return order <= 28 ? 0 :
 
 // One CTA: stable counting sort of the subframes by class into p.order_index; every class segment
 // starts on a warp boundary (4 subframes), widest class first; gaps hold 0xffffffff (pre-set by the host side).
-__global__ void __launch_bounds__(1024) k_decode_classify(DecodeParams p)
+// Two launches of 1024 subframes per CTA (coalesced descriptor loads in both):
+//   k_decode_class_counts  CTA b: how many of its subframes fall in each class -> tmp[b] (classes 0|1 and 2|3 packed
+//                          as the 32-bit halves of two words)
+//   k_decode_classify      CTA b: totals of all CTAs (-> where each class segment starts; widest class first) + counts
+//                          of the CTAs before it + a block scan -> order_index.  Ascending subframe order inside a
+//                          class is kept (stable), so the two subframes of a stereo frame stay neighbours.
+// tmp is the head of the Rice decoder's scratch, which is not in use yet.
+struct ClassCounts {
+    unsigned long long c01, c23;
+};
+__device__ __forceinline__ ClassCounts class_one(int c)
 {
-    __shared__ unsigned long long warp_tot[32]; // four 16-bit class counts per warp
-    __shared__ uint32_t run[4];                 // next free unit slot per class
-    __shared__ uint32_t count[4];
-    const uint32_t gsz = 1;
+    ClassCounts v;
+    const unsigned long long one = 1ull << (32 * (c & 1));
+    v.c01 = (c >> 1) ? 0ull : one;
+    v.c23 = (c >> 1) ? one : 0ull;
+    return v;
+}
+__device__ __forceinline__ uint32_t class_get(const ClassCounts &v, int c)
+{
+    return (uint32_t)(((c >> 1) ? v.c23 : v.c01) >> (32 * (c & 1)));
+}
+__device__ __forceinline__ int subframe_class(const DecodeParams &p, uint32_t u)
+{
+    const int order = p.descs[u].lpc_order;
+    return order_class(order > kMaxOrder ? 0 : order);
+}
+
+__global__ void __launch_bounds__(kScanTile) k_decode_class_counts(DecodeParams p, ClassCounts *tmp)
+{
+    __shared__ ClassCounts warp_cnt[32];
     const uint32_t n_units = p.n_frames * p.channels;
+    const uint32_t u = blockIdx.x * kScanTile + threadIdx.x;
+    ClassCounts v = {0ull, 0ull};
+    if (u < n_units)
+        v = class_one(subframe_class(p, u));
+    v.c01 = warp_sum_u64(v.c01);
+    v.c23 = warp_sum_u64(v.c23);
+    if (lane_id() == 0)
+        warp_cnt[warp_id()] = v;
+    __syncthreads();
+    if (warp_id() == 0) {
+        v = warp_cnt[lane_id()];
+        v.c01 = warp_sum_u64(v.c01);
+        v.c23 = warp_sum_u64(v.c23);
+        if (lane_id() == 0)
+            tmp[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kScanTile) k_decode_classify(DecodeParams p, const ClassCounts *tmp)
+{
+    __shared__ unsigned long long warp_tot[2][32];
+    __shared__ ClassCounts total, before;
+    const uint32_t n_units = p.n_frames * p.channels;
+    const uint32_t u = blockIdx.x * kScanTile + threadIdx.x;
     const int lane = lane_id(), warp = warp_id();
-    auto unit_class = [&](uint32_t u) {
-        int order = 0;
-        for (uint32_t j = 0; j < gsz; j++) {
-            const int o = p.descs[(size_t)u * gsz + j].lpc_order;
-            order = o > order ? o : order;
+    if (warp == 0) {
+        ClassCounts all = {0ull, 0ull}, pre = {0ull, 0ull};
+        for (uint32_t b = lane; b < gridDim.x; b += 32) {
+            const ClassCounts v = tmp[b];
+            all.c01 += v.c01, all.c23 += v.c23;
+            if (b < blockIdx.x)
+                pre.c01 += v.c01, pre.c23 += v.c23;
         }
-        return order_class(order > kMaxOrder ? 0 : order);
-    };
-    if (threadIdx.x < 4)
-        count[threadIdx.x] = 0;
-    __syncthreads();
-    uint32_t mine[4] = {0, 0, 0, 0};
-    for (uint32_t u = threadIdx.x; u < n_units; u += 1024)
-        mine[unit_class(u)]++;
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (mine[c])
-            atomicAdd(&count[c], mine[c]);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t per_warp = 4 / gsz; // units per warp
-        // widest class first: a synthesis warp runs its four subframes start to finish (hundreds of
-        // microseconds), so the longest-running warps must be scheduled first and the short ones
-        // left to fill the tail
-        uint32_t base = 0;
-        for (int c = 3; c >= 0; c--) {
-            run[c] = base;
-            base += (count[c] + per_warp - 1) / per_warp * per_warp;
-        }
+        all.c01 = warp_sum_u64(all.c01), all.c23 = warp_sum_u64(all.c23);
+        pre.c01 = warp_sum_u64(pre.c01), pre.c23 = warp_sum_u64(pre.c23);
+        if (lane == 0)
+            total = all, before = pre;
     }
-    __syncthreads();
-    for (uint32_t tile = 0; tile < n_units; tile += 1024) {
-        const uint32_t u = tile + threadIdx.x;
-        const bool have = u < n_units;
-        const int c = have ? unit_class(u) : 0;
-        unsigned long long packed = have ? 1ull << (16 * c) : 0ull, incl = packed;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(kFull, w, o);
-                if (lane >= o)
-                    w += t;
-            }
-            warp_tot[lane] = w; // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned long long before = (warp ? warp_tot[warp - 1] : 0ull) + incl - packed;
-        if (have) {
-            const uint32_t slot = run[c] + (uint32_t)((before >> (16 * c)) & 0xffffu);
-            for (uint32_t j = 0; j < gsz; j++)
-                p.order_index[(size_t)slot * gsz + j] = u * gsz + j;
-        }
-        __syncthreads();
-        if (threadIdx.x < 4)
-            run[threadIdx.x] += (uint32_t)((warp_tot[31] >> (16 * threadIdx.x)) & 0xffffu);
-        __syncthreads();
-    }
+    const bool have = u < n_units;
+    const int c = have ? subframe_class(p, u) : 0;
+    ClassCounts mine = {0ull, 0ull};
+    if (have)
+        mine = class_one(c);
+    ClassCounts incl;
+    incl.c01 = block_scan_inclusive_u64(mine.c01, warp_tot[0]); // the barriers in here also publish total / before
+    incl.c23 = block_scan_inclusive_u64(mine.c23, warp_tot[1]);
+    if (!have)
+        return;
+    // widest class first: a synthesis warp runs its four subframes start to finish (hundreds of microseconds), so
+    // the longest-running warps must be scheduled first and the short ones left to fill the tail; every class
+    // segment starts on a multiple of the four subframes a warp takes
+    uint32_t base = 0;
+    for (int k = 3; k > c; k--)
+        base += (class_get(total, k) + 3u) / 4u * 4u;
+    ClassCounts excl;
+    excl.c01 = before.c01 + incl.c01 - mine.c01;
+    excl.c23 = before.c23 + incl.c23 - mine.c23;
+    p.order_index[base + class_get(excl, c)] = u;
 }
 
 // K6, batch form: one warp = four subframes of one predictor-order class (stereo: two whole

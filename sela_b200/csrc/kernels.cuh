@@ -1,14 +1,14 @@
 // kernels.cuh -- the __global__ kernels of the SELA hot path (sm_100a).
 //
-//   k_encode<STEREO>     fused encode of one scan unit per CTA: PCM -> autocorrelation
-//                        -> Schur -> quantise -> step-up -> FIR -> Rice size -> arena
-//                        offset (decoupled look-back) -> Rice pack + descriptor.
-//                        STEREO: unit = frame, 3 warps (ch0, ch1, ch0-ch1);
-//                        otherwise unit = subframe, 1 warp.
-//   k_rice_decode        K5: one lane per Rice stream (reflection or residue streams).
-//   k_synthesise         K6: CTA per frame, warp per subframe: step-up + IIR, difference
-//                        reconstruction, interleave to int16 PCM.
-//   k_lpc_residues / k_lpc_samples / k_rice_encode   stage-level entry points.
+//   encode   k_encode_units<STEREO> (warp per analysis unit: PCM -> ... -> Rice pack into a private slot)
+//            k_encode_sizes + k_encode_scan (stereo decision, prefix sum, descriptors)
+//            k_encode_gather / k_encode_gather_container (slot -> word arena / .sela byte stream)
+//   decode   k_container_unpack (.sela bytes -> word arena)
+//            k_decode_class_counts + k_decode_classify (subframes grouped by predictor-order class)
+//            k_rice_decode<RING,BATCH> (lane per stream: reflection streams, flagged residue streams)
+//            k_rice_split_index / k_rice_decode_vc (rice_vs.cuh: residue streams, lane per part of a stream)
+//            k_synthesise_quad (+ k_diff_fixup; k_synthesise for frames the batch kernel declines)
+//   stage-level entry points   k_lpc_residues, k_lpc_samples, k_rice_encode, k_rice_decode_streams
 #pragma once
 
 #include "lpc.cuh"
@@ -19,15 +19,15 @@ namespace selab200 {
 
 // ------------------------------------------------------------------ encode --
 //
-// Three launches, no inter-CTA dependency anywhere:
+// Four launches, no inter-CTA dependency inside any of them:
 //   k_encode_units   one WARP per analysis unit (a channel, or for stereo the three
 //                    candidates ch0 / ch1 / ch0-ch1 of a frame): PCM -> autocorrelation ->
 //                    Schur -> quantise -> step-up -> FIR -> Rice parameter search -> Rice
 //                    pack into the unit's private slot of a scratch arena + a 32-byte
 //                    unit record.  No barriers, no atomics between units.
-//   k_encode_scan    one CTA: stereo decision (difference wins iff strictly fewer words,
-//                    src/frame/frame_encoder.cpp:63-72), exclusive prefix sum of the chosen
-//                    sizes in file order, descriptors, total.
+//   k_encode_sizes,  1024 subframes per CTA: stereo decision (difference wins iff strictly fewer
+//   k_encode_scan    words, src/frame/frame_encoder.cpp:63-72), exclusive prefix sum of the chosen
+//                    sizes in file order, descriptors, total (see there).
 //   k_encode_gather  one warp per emitted subframe: slot -> final arena offset.
 
 constexpr uint32_t kSlotWords = 1600;     // per-unit scratch slot (refl words first, then residue words)
@@ -660,7 +660,7 @@ __global__ void k_synthesise(DecodeParams p)
 // evenly over 17..100) that removes about a quarter of the multiplies.
 __device__ __forceinline__ int order_class(int order) { return order <= 28 ? 0 : order <= 56 ? 1 : 2; }
 
-// One CTA: stable counting sort of the subframes by class into p.order_index; every class segment
+// Stable counting sort of the subframes by class into p.order_index; every class segment
 // starts on a warp boundary (4 subframes), widest class first; gaps hold 0xffffffff (pre-set by the host side).
 // Two launches of 1024 subframes per CTA (coalesced descriptor loads in both):
 //   k_decode_class_counts  CTA b: how many of its subframes fall in each class -> tmp[b] (classes 0|1 and 2|3 packed

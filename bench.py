@@ -594,9 +594,10 @@ def run_ours(args, rank, world, local_rank):
                     "encode_ms": split[0] / e2e_steps * 1e3, "decode_ms": split[1] / e2e_steps * 1e3,
                     "pcie_probe": pcie,
                     "copy_floor_ms": None if not pcie or "error" in pcie else
-                    (h2d / (pcie["h2d_gbs"] * 1e6) + d2h / (pcie["d2h_gbs"] * 1e6)) / 2,
-                    "note": "copy_floor_ms = (H2D bytes / probed H2D rate + D2H bytes / probed D2H rate) / 2: the two "
-                            "directions overlap, so a step cannot be faster than about this"},
+                    (max(n_samples * 2 / pcie["h2d_gbs"], (used.value * 4 + n_frames * CHANNELS * 32) / pcie["d2h_gbs"]) +
+                     max((used.value * 4 + n_frames * CHANNELS * 32) / pcie["h2d_gbs"], n_samples * 2 / pcie["d2h_gbs"])) / 1e6,
+                    "note": "copy_floor_ms: the two calls of a step run one after the other and each overlaps its own upload and "
+                            "download, so a step cannot beat max(PCM up, words down) + max(words up, PCM down) at the probed rates"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",

@@ -762,8 +762,12 @@ struct QuadSmem {
     IirSmem ii[4];
     double t[104];
     CoefSmem cf[4];
-    int32_t stage[4][2][16];
+    // staging rows [2][16] of the four quarters at word offsets 0, 48, 104, 152: the four writer lanes (one per
+    // quarter, same row and column) then hit banks 0 / 16 / 8 / 24 apart, and the 8-byte reads of a half-warp
+    // (two quarters) cover 32 distinct banks; a plain [4][2][16] puts all four writers on one bank
+    int32_t stage[184];
 };
+__device__ __forceinline__ int quad_stage_offset(int q) { return 48 * q + 8 * (q >> 1); }
 
 __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
 {
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(32) k_synthesise_quad(DecodeParams p)
     // ---- recurrence + output ----
     QuadIo io;
     io.res = p.ws_res + (size_t)(exists ? sub : 0) * kFrame;
-    io.stage = &sm.stage[q][0][0];
+    io.stage = sm.stage + quad_stage_offset(q);
     const bool diff = proc && mine.subframe_type == 1;
     const uint32_t channel = mine.channel;
     int16_t *out = p.pcm_out + (size_t)frame * kFrame * ch;

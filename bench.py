@@ -205,6 +205,24 @@ def pcie_probe(dev, nbytes=128 << 20):
         b.record()
         torch.cuda.synchronize(dev)
         res[name] = 3 * nbytes / a.elapsed_time(b) / 1e6
+    # both directions at once, as the pipelined calls drive the link (on some boxes each direction then runs slower)
+    h2, d2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.cuda.stream(s_up):
+        ev[0].record()
+        for _ in range(3):
+            d.copy_(h, non_blocking=True)
+        ev[1].record()
+    with torch.cuda.stream(s_down):
+        ev[2].record()
+        for _ in range(3):
+            h2.copy_(d2, non_blocking=True)
+        ev[3].record()
+    torch.cuda.synchronize(dev)
+    res["h2d_gbs_both_directions"] = 3 * nbytes / ev[0].elapsed_time(ev[1]) / 1e6
+    res["d2h_gbs_both_directions"] = 3 * nbytes / ev[2].elapsed_time(ev[3]) / 1e6
     return res
 
 

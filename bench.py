@@ -615,7 +615,9 @@ def run_ours(args, rank, world, local_rank):
                     (max(n_samples * 2 / pcie["h2d_gbs"], (used.value * 4 + n_frames * CHANNELS * 32) / pcie["d2h_gbs"]) +
                      max((used.value * 4 + n_frames * CHANNELS * 32) / pcie["h2d_gbs"], n_samples * 2 / pcie["d2h_gbs"])) / 1e6,
                     "note": "copy_floor_ms: the two calls of a step run one after the other and each overlaps its own upload and "
-                            "download, so a step cannot beat max(PCM up, words down) + max(words up, PCM down) at the probed rates"},
+                            "download, so a step cannot beat max(PCM up, words down) + max(words up, PCM down) at the one-direction rates; "
+                            "pcie_probe.*_both_directions = each direction's rate while the other is busy, which is what the "
+                            "pipelined calls see most of the time"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_encode_units<stereo> (fused analysis+FIR+Rice; + scan + gather launches)", "bound": "hbm",
